@@ -1,0 +1,136 @@
+// common.cuh -- shared declarations of libprimalcr_b200 (sm_100a only; no CPU fallback).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <stdexcept>
+
+namespace pcr {
+
+typedef long long i64;
+
+// ------------------------------------------------------------------ errors
+struct Error : public std::runtime_error {
+    int code;
+    Error(int c, const std::string &w) : std::runtime_error(w), code(c) {}
+};
+
+#define PCR_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            char _b[512];                                                                      \
+            snprintf(_b, sizeof(_b), "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e),       \
+                     __FILE__, __LINE__, cudaGetErrorString(_e));                              \
+            throw pcr::Error(-2, _b);                                                          \
+        }                                                                                      \
+    } while (0)
+
+#define PCR_REQUIRE(cond, msg)                                                                 \
+    do { if (!(cond)) throw pcr::Error(-1, std::string(msg)); } while (0)
+
+// ------------------------------------------------------------------ profiler: CUDA events around every launch
+struct Profiler {
+    struct Rec { int id; cudaEvent_t a, b; double bytes; };
+    struct Acc { std::string name; double ms = 0; i64 launches = 0; double bytes = 0; };
+    bool enabled = false;
+    i64 launches = 0;                 // counted whether or not event timing is on
+    std::vector<Rec> pending;
+    std::vector<Acc> acc;
+    std::map<std::string, int> ids;
+    std::vector<cudaEvent_t> pool;
+
+    int id_of(const char *name) {
+        auto it = ids.find(name);
+        if (it != ids.end()) return it->second;
+        int id = (int)acc.size();
+        ids[name] = id;
+        Acc a; a.name = name; acc.push_back(a);
+        return id;
+    }
+    cudaEvent_t get_event() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; PCR_CUDA(cudaEventCreate(&e)); return e;
+    }
+    void begin(const char *name, cudaStream_t s, double bytes) {
+        ++launches;
+        if (!enabled) return;
+        Rec r; r.id = id_of(name); r.a = get_event(); r.b = get_event(); r.bytes = bytes;
+        PCR_CUDA(cudaEventRecord(r.a, s));
+        pending.push_back(r);
+    }
+    void end(cudaStream_t s) {
+        if (!enabled) return;
+        PCR_CUDA(cudaEventRecord(pending.back().b, s));
+    }
+    void resolve() {   // caller has synchronised the stream
+        for (auto &r : pending) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+                acc[r.id].ms += ms; acc[r.id].launches += 1; acc[r.id].bytes += r.bytes;
+            }
+            pool.push_back(r.a); pool.push_back(r.b);
+        }
+        pending.clear();
+    }
+    void reset() { resolve(); for (auto &a : acc) { a.ms = 0; a.launches = 0; a.bytes = 0; } }
+    ~Profiler() { for (auto &r : pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } for (auto e : pool) cudaEventDestroy(e); }
+};
+
+// RAII device buffer bookkeeping
+struct DevPool {
+    std::vector<void *> ptrs;
+    i64 bytes = 0;
+    template <typename T> T *alloc(size_t n) {
+        void *p = nullptr;
+        size_t b = (n > 0 ? n : 1) * sizeof(T);
+        PCR_CUDA(cudaMalloc(&p, b));
+        ptrs.push_back(p); bytes += (i64)b;
+        return (T *)p;
+    }
+    void release() { for (void *p : ptrs) cudaFree(p); ptrs.clear(); bytes = 0; }
+    ~DevPool() { release(); }
+};
+
+// ------------------------------------------------------------------ a ratings set on the device (CSR by user)
+struct DevCsr {
+    i64 d1 = 0, nnz = 0;
+    i64 *row_ptr = nullptr;      // [d1+1]
+    int32_t *item = nullptr;     // [nnz] item id
+    int32_t *user = nullptr;     // [nnz] owning user (local id)
+    double *rating = nullptr;    // [nnz] exact rating (eval, Primal-CR)
+    uint8_t *level = nullptr;    // [nnz] global level index of lround(rating) (Primal-CR++)
+    std::vector<i64> h_row_ptr;  // host copy
+    // size classes: users with 0 < len <= S_CAP, S_CAP < len <= L_CAP, len > L_CAP
+    int32_t *cls_users[3] = {nullptr, nullptr, nullptr};
+    int n_cls[3] = {0, 0, 0};
+    i64 *heavy_off = nullptr;    // [d1] offset into the heavy scratch arrays, -1 if not heavy
+    i64 heavy_total = 0;         // sum over heavy users of (len + 1)
+    i64 *heavy_begin = nullptr, *heavy_end = nullptr;  // [n_cls[2]] absolute segment bounds (CUB segmented sort)
+    i64 max_len = 0;
+    // pair-tile work items (Primal-CR pair kernels and pairwise-error evaluation)
+    int32_t *pt_user = nullptr; int32_t *pt_j0 = nullptr; i64 n_pt = 0;
+    i64 *pt_ptr = nullptr;       // [d1+1] first work item of each user
+    // row-sum work units over this CSR (segments = users)
+    int32_t *un_seg = nullptr; i64 *un_start = nullptr; i64 n_units = 0;   // un_start[n_units+1]
+    i64 *seg_unit_ptr = nullptr; // [d1+1]
+};
+
+struct SortedMeta {          // per rating, in (user, ascending score) order
+    double *s = nullptr;     // sorted scores
+    int32_t *pos = nullptr;  // CSR position of the rating that sits at this sorted slot
+    uint8_t *lev = nullptr;  // its level
+    int32_t *ub = nullptr, *lb = nullptr;      // window pointers (local to the user)
+    int32_t *cnt_lo = nullptr, *cnt_hi = nullptr;
+};
+
+static const int S_CAP = 1024;   // block class  (256 threads, shared memory)
+static const int L_CAP = 4096;   // large class  (1024 threads, shared memory)
+static const int ROWSUM_CHUNK = 256;
+static const int PAIR_TJ = 256;  // j elements per pair work item
+static const int MAX_LEVELS = 32;
+
+}  // namespace pcr

@@ -1,0 +1,976 @@
+// engine.cu -- host orchestration of the Primal-CR / Primal-CR++ alternating Newton-CG loop on one GPU,
+// and the C ABI declared in include/primalcr.h.
+//
+// Control flow mirrors the reference exactly:
+//   update_V  : pcrpp.cpp:415-444 (pcr.cpp:279-330) with solve_delta_new :335-358
+//   update_U  : pcrpp.cpp:818-838 / update_u_new :779-815 (pcr.cpp:587-611 / :523-585), batched over users
+//   driver    : pcrpp.cpp:841-901 / pcr.cpp:616-704
+// Arithmetic runs in the kernels of k_core.cu / k_pairs.cu.  There is no CPU implementation of any stage.
+#include "kernels.h"
+#include "../../include/primalcr.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <dlfcn.h>
+#include <random>
+
+// ---- NCCL, bound at run time (only needed when world > 1) -----------------------------------------
+typedef struct { char internal[128]; } pcr_ncclUniqueId;
+typedef void *pcr_ncclComm_t;
+enum { PCR_NCCL_FLOAT64 = 8, PCR_NCCL_SUM = 0 };
+
+namespace pcr {
+
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(pcr_ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(pcr_ncclComm_t *, int, pcr_ncclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, pcr_ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(pcr_ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (h) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+    }
+};
+static NcclApi g_nccl;
+
+static thread_local std::string g_last_error;
+
+static int ceil4(int k) { return (k + 3) & ~3; }
+
+struct Engine {
+    primalcr_config cfg;
+    cudaStream_t stream = nullptr;
+    Profiler prof;
+    DevPool pool;
+    Ctx ctx;
+    int sms = 148;
+    int k = 0, ld = 0, T = 0;
+    i64 d1 = 0, d2 = 0;
+    std::vector<i64> levels;
+    bool levels_user_set = false;
+    DevCsr X, XT;
+    bool has_train = false, has_test = false, has_factors = false;
+    // CSC of the training set (by item)
+    i64 *col_ptr = nullptr; int32_t *csc_user = nullptr, *csc2csr = nullptr;
+    int32_t *cu_seg = nullptr; i64 *cu_start = nullptr; i64 n_cunits = 0; i64 *col_unit_ptr = nullptr;
+    // factors (padded leading dimension ld)
+    double *U = nullptr, *V = nullptr;
+    // per-rating work buffers
+    double *m = nullptr, *b = nullptr, *cbuf = nullptr;
+    SortedMeta meta;
+    int32_t *iota = nullptr;
+    bool scores_valid = false, meta_valid = false;
+    // heavy-user scratch
+    double *h_v = nullptr, *h_p1 = nullptr, *h_p2 = nullptr, *h_acc = nullptr; int32_t *h_cnt = nullptr;
+    void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+    // V-side vectors [d2 x ld]
+    double *g = nullptr, *delta = nullptr, *rr = nullptr, *p = nullptr, *Hp = nullptr, *Vnew = nullptr;
+    double *partial = nullptr;
+    double *red_partials = nullptr, *slots = nullptr; double *h_slots = nullptr;
+    int *h_counters = nullptr;
+    UState us;
+    uint8_t *has_pairs = nullptr;
+    double *obj_item = nullptr;
+    i64 *stats_dev = nullptr; i64 *h_stats = nullptr;
+    // evaluation buffers (sized for max(train, test))
+    double *ev_score_t = nullptr; i64 *ev_err_item = nullptr;
+    double *ev_a = nullptr, *ev_b = nullptr, *ev_c = nullptr, *ev_d = nullptr;
+    // comm
+    int rank = 0, world = 1; pcr_ncclComm_t comm = nullptr;
+    primalcr_counters counters;
+    int v_accepted = 1;
+
+    explicit Engine(const primalcr_config &c) : cfg(c) {
+        memset(&counters, 0, sizeof(counters));
+        memset(&us, 0, sizeof(us));
+        PCR_REQUIRE(cfg.solver == 1 || cfg.solver == 2, "solver must be 1 (Primal-CR) or 2 (Primal-CR++)");
+        PCR_REQUIRE(cfg.k >= 1 && cfg.k <= 512, "rank k out of range [1, 512]");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Error(PRIMALCR_ECUDA, "no CUDA device available: libprimalcr_b200 has no CPU fallback");
+        PCR_REQUIRE(cfg.device >= 0 && cfg.device < ndev, "bad device ordinal");
+        PCR_CUDA(cudaSetDevice(cfg.device));
+        cudaDeviceProp prop;
+        PCR_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
+        sms = prop.multiProcessorCount;
+        PCR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        ctx.stream = stream; ctx.prof = &prof; ctx.sms = sms;
+        k = cfg.k; ld = ceil4(k);
+        PCR_CUDA(cudaMallocHost(&h_slots, sizeof(double) * 32));
+        PCR_CUDA(cudaMallocHost(&h_counters, sizeof(int) * 4));
+        PCR_CUDA(cudaMallocHost(&h_stats, sizeof(i64) * 8));
+        slots = pool.alloc<double>(32);
+        red_partials = pool.alloc<double>(1024);
+        us.counters = pool.alloc<int>(4);
+        stats_dev = pool.alloc<i64>(8);
+    }
+    ~Engine() {
+        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        cudaSetDevice(cfg.device);
+        if (stream) cudaStreamSynchronize(stream);
+        prof.resolve();
+        pool.release();
+        if (h_slots) cudaFreeHost(h_slots);
+        if (h_counters) cudaFreeHost(h_counters);
+        if (h_stats) cudaFreeHost(h_stats);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    void bind() { PCR_CUDA(cudaSetDevice(cfg.device)); }
+    void sync() { PCR_CUDA(cudaStreamSynchronize(stream)); prof.resolve(); }
+
+    template <typename Tp> Tp *upload(const Tp *h, size_t n) {
+        Tp *d = pool.alloc<Tp>(n);
+        if (n) PCR_CUDA(cudaMemcpyAsync(d, h, sizeof(Tp) * n, cudaMemcpyHostToDevice, stream));
+        return d;
+    }
+    template <typename Tp> Tp *upload_vec(const std::vector<Tp> &v) { return upload(v.data(), v.size()); }
+
+    // ------------------------------------------------------------------ data
+    void build_csr_common(DevCsr &C, i64 d1_, i64 nnz, const i64 *row_ptr, const int32_t *item, const double *rating) {
+        C.d1 = d1_; C.nnz = nnz;
+        C.h_row_ptr.assign(row_ptr, row_ptr + d1_ + 1);
+        PCR_REQUIRE(C.h_row_ptr[0] == 0 && C.h_row_ptr[d1_] == nnz, "row_ptr must start at 0 and end at nnz");
+        PCR_REQUIRE(nnz < ((i64)1 << 31) - 64, "nnz per engine must be < 2^31 (shard the users)");
+        C.row_ptr = upload(row_ptr, (size_t)d1_ + 1);
+        C.item = upload(item, (size_t)nnz);
+        C.rating = upload(rating, (size_t)nnz);
+        C.user = pool.alloc<int32_t>((size_t)nnz);
+        k_expand_users(ctx, C.row_ptr, d1_, nnz, C.user);
+        // pair-tile work items
+        std::vector<int32_t> ptu, ptj; std::vector<i64> ptp((size_t)d1_ + 1, 0);
+        C.max_len = 0;
+        for (i64 u = 0; u < d1_; ++u) {
+            const i64 len = C.h_row_ptr[u + 1] - C.h_row_ptr[u];
+            PCR_REQUIRE(len >= 0, "row_ptr must be non-decreasing");
+            C.max_len = std::max(C.max_len, len);
+            ptp[u] = (i64)ptu.size();
+            for (i64 j0 = 0; j0 < len; j0 += PAIR_TJ) { ptu.push_back((int32_t)u); ptj.push_back((int32_t)j0); }
+        }
+        ptp[d1_] = (i64)ptu.size();
+        C.n_pt = (i64)ptu.size();
+        C.pt_user = upload_vec(ptu); C.pt_j0 = upload_vec(ptj); C.pt_ptr = upload_vec(ptp);
+        sync();   // host vectors above go out of scope
+    }
+
+    static void make_units(const std::vector<i64> &ptr, std::vector<int32_t> &seg, std::vector<i64> &start,
+                           std::vector<i64> &seg_unit_ptr) {
+        const i64 nseg = (i64)ptr.size() - 1;
+        seg.clear(); start.clear(); seg_unit_ptr.assign((size_t)nseg + 1, 0);
+        for (i64 s = 0; s < nseg; ++s) {
+            seg_unit_ptr[s] = (i64)seg.size();
+            for (i64 b = ptr[s]; b < ptr[s + 1]; b += ROWSUM_CHUNK) { seg.push_back((int32_t)s); start.push_back(b); }
+        }
+        seg_unit_ptr[nseg] = (i64)seg.size();
+        start.push_back(ptr[nseg]);
+    }
+
+    void set_levels(const i64 *vals, int n) {
+        PCR_REQUIRE(n >= 1 && n <= MAX_LEVELS, "number of rating levels must be in [1, 32]");
+        levels.assign(vals, vals + n);
+        for (int i = 1; i < n; ++i) PCR_REQUIRE(levels[i] > levels[i - 1], "level table must be strictly ascending");
+        levels_user_set = true;
+    }
+
+    void set_train(i64 d1_, i64 d2_, i64 nnz, const i64 *row_ptr, const int32_t *item, const double *rating) {
+        bind();
+        PCR_REQUIRE(!has_train, "training set already loaded (one data set per engine)");
+        PCR_REQUIRE(d1_ >= 0 && d2_ >= 1 && nnz >= 0, "bad sizes");
+        d1 = d1_; d2 = d2_;
+        build_csr_common(X, d1_, nnz, row_ptr, item, rating);
+        // ---- rating levels (find_levels pcrpp.cpp:38-49, as one global order-preserving table)
+        if (!levels_user_set) {
+            i64 lo = 0, hi = 0; bool any = false;
+            std::vector<i64> distinct;
+            for (i64 e = 0; e < nnz; ++e) {
+                const i64 v = llround(rating[e]);
+                if (!any) { lo = hi = v; any = true; }
+                if (v < lo) lo = v; if (v > hi) hi = v;
+                if (hi - lo >= 4096) break;
+            }
+            if (!any) { lo = hi = 0; }
+            if (hi - lo + 1 <= MAX_LEVELS) {
+                // a superset of the levels present is harmless: an empty level contributes 0*x - 0
+                for (i64 v = lo; v <= hi; ++v) distinct.push_back(v);
+            } else {
+                for (i64 e = 0; e < nnz; ++e) {
+                    const i64 v = llround(rating[e]);
+                    auto it = std::lower_bound(distinct.begin(), distinct.end(), v);
+                    if (it == distinct.end() || *it != v) distinct.insert(it, v);
+                    PCR_REQUIRE((int)distinct.size() <= MAX_LEVELS, "more than 32 distinct rating levels");
+                }
+            }
+            levels = distinct;
+        }
+        T = (int)levels.size();
+        i64 *tab = upload_vec(levels);
+        int *bad = pool.alloc<int>(1);
+        PCR_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), stream));
+        X.level = pool.alloc<uint8_t>((size_t)nnz);
+        k_levels(ctx, X.rating, nnz, tab, T, X.level, bad);
+        PCR_CUDA(cudaMemcpyAsync(h_counters, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        sync();
+        PCR_REQUIRE(h_counters[0] == 0, "a rating rounds to a level that is not in the level table");
+        // ---- size classes, heavy scratch
+        std::vector<int32_t> cls[3];
+        std::vector<i64> hoff((size_t)d1, -1), hb, he;
+        i64 htot = 0;
+        for (i64 u = 0; u < d1; ++u) {
+            const i64 len = X.h_row_ptr[u + 1] - X.h_row_ptr[u];
+            if (len == 0) continue;
+            if (len <= S_CAP) cls[0].push_back((int32_t)u);
+            else if (len <= L_CAP) cls[1].push_back((int32_t)u);
+            else { cls[2].push_back((int32_t)u); hoff[u] = htot; htot += len + 1; hb.push_back(X.h_row_ptr[u]); he.push_back(X.h_row_ptr[u + 1]); }
+        }
+        for (int q = 0; q < 3; ++q) { X.n_cls[q] = (int)cls[q].size(); X.cls_users[q] = upload_vec(cls[q]); }
+        X.heavy_off = upload_vec(hoff); X.heavy_total = htot;
+        X.heavy_begin = upload_vec(hb); X.heavy_end = upload_vec(he);
+        h_v = pool.alloc<double>((size_t)htot); h_p1 = pool.alloc<double>((size_t)htot);
+        h_p2 = pool.alloc<double>((size_t)htot); h_acc = pool.alloc<double>((size_t)htot);
+        h_cnt = pool.alloc<int32_t>((size_t)htot);
+        // ---- row-sum work units over the CSR
+        std::vector<int32_t> useg; std::vector<i64> ustart, supt;
+        make_units(X.h_row_ptr, useg, ustart, supt);
+        X.n_units = (i64)useg.size();
+        X.un_seg = upload_vec(useg); X.un_start = upload_vec(ustart); X.seg_unit_ptr = upload_vec(supt);
+        sync();
+        // ---- CSC by item + its work units
+        col_ptr = pool.alloc<i64>((size_t)d2 + 1);
+        csc2csr = pool.alloc<int32_t>((size_t)nnz); csc_user = pool.alloc<int32_t>((size_t)nnz);
+        k_build_csc(ctx, pool, X.item, X.user, nnz, d2, col_ptr, csc2csr, csc_user);
+        std::vector<i64> h_col((size_t)d2 + 1);
+        PCR_CUDA(cudaMemcpyAsync(h_col.data(), col_ptr, sizeof(i64) * ((size_t)d2 + 1), cudaMemcpyDeviceToHost, stream));
+        sync();
+        PCR_REQUIRE(h_col[d2] == nnz, "item id out of range [0, d2)");
+        std::vector<int32_t> cseg; std::vector<i64> cstart, csup;
+        make_units(h_col, cseg, cstart, csup);
+        n_cunits = (i64)cseg.size();
+        cu_seg = upload_vec(cseg); cu_start = upload_vec(cstart); col_unit_ptr = upload_vec(csup);
+        // ---- work buffers
+        m = pool.alloc<double>((size_t)nnz); b = pool.alloc<double>((size_t)nnz); cbuf = pool.alloc<double>((size_t)nnz);
+        meta.s = pool.alloc<double>((size_t)nnz); meta.pos = pool.alloc<int32_t>((size_t)nnz);
+        meta.lev = pool.alloc<uint8_t>((size_t)nnz);
+        meta.ub = pool.alloc<int32_t>((size_t)nnz); meta.lb = pool.alloc<int32_t>((size_t)nnz);
+        meta.cnt_lo = pool.alloc<int32_t>((size_t)nnz); meta.cnt_hi = pool.alloc<int32_t>((size_t)nnz);
+        iota = pool.alloc<int32_t>((size_t)nnz);
+        k_iota32(ctx, iota, nnz);
+        const size_t vn = (size_t)d2 * ld, un = (size_t)d1 * ld;
+        U = pool.alloc<double>(un); V = pool.alloc<double>(vn);
+        g = pool.alloc<double>(vn); delta = pool.alloc<double>(vn); rr = pool.alloc<double>(vn);
+        p = pool.alloc<double>(vn); Hp = pool.alloc<double>(vn); Vnew = pool.alloc<double>(vn);
+        partial = pool.alloc<double>((size_t)std::max(X.n_units, n_cunits) * ld);
+        us.g = pool.alloc<double>(un); us.delta = pool.alloc<double>(un); us.rr = pool.alloc<double>(un);
+        us.p = pool.alloc<double>(un); us.Hp = pool.alloc<double>(un); us.Unew = pool.alloc<double>(un);
+        us.err = pool.alloc<double>((size_t)d1); us.step = pool.alloc<double>((size_t)d1);
+        us.prev_obj = pool.alloc<double>((size_t)d1); us.obj_new = pool.alloc<double>((size_t)d1);
+        us.loss = pool.alloc<double>((size_t)d1);
+        us.cg_active = pool.alloc<uint8_t>((size_t)d1); us.ls_active = pool.alloc<uint8_t>((size_t)d1);
+        us.skipped = pool.alloc<uint8_t>((size_t)d1);
+        us.cg_its = pool.alloc<int32_t>((size_t)d1); us.ls_trials = pool.alloc<int32_t>((size_t)d1);
+        k_fill(ctx, us.loss, d1, 0.0);
+        has_pairs = pool.alloc<uint8_t>((size_t)d1);
+        k_has_pairs(ctx, X, has_pairs);
+        obj_item = pool.alloc<double>((size_t)X.n_pt);
+        ensure_eval_buffers(X);
+        sync();
+        has_train = true;
+    }
+
+    i64 ev_cap_pt = 0, ev_cap_d1 = 0, ev_cap_nnz = 0;
+    void ensure_eval_buffers(const DevCsr &C) {
+        if (C.n_pt > ev_cap_pt) { ev_err_item = pool.alloc<i64>((size_t)C.n_pt); ev_cap_pt = C.n_pt; }
+        if (C.d1 > ev_cap_d1 || ev_a == nullptr) {
+            ev_a = pool.alloc<double>((size_t)C.d1); ev_b = pool.alloc<double>((size_t)C.d1);
+            ev_c = pool.alloc<double>((size_t)C.d1); ev_d = pool.alloc<double>((size_t)C.d1); ev_cap_d1 = C.d1;
+        }
+    }
+
+    void set_test(i64 nnz, const i64 *row_ptr, const int32_t *item, const double *rating) {
+        bind();
+        PCR_REQUIRE(has_train, "load the training set first");
+        PCR_REQUIRE(!has_test, "test set already loaded");
+        build_csr_common(XT, d1, nnz, row_ptr, item, rating);
+        ev_score_t = pool.alloc<double>((size_t)nnz);
+        ensure_eval_buffers(XT);
+        has_test = nnz > 0;
+    }
+
+    void put_matrix(const double *h, i64 rows, double *dst) {
+        if (rows == 0) return;
+        if (ld == k) {
+            PCR_CUDA(cudaMemcpyAsync(dst, h, sizeof(double) * (size_t)rows * k, cudaMemcpyHostToDevice, stream));
+        } else {
+            double *tmp = nullptr;
+            PCR_CUDA(cudaMalloc(&tmp, sizeof(double) * (size_t)rows * k));
+            PCR_CUDA(cudaMemcpyAsync(tmp, h, sizeof(double) * (size_t)rows * k, cudaMemcpyHostToDevice, stream));
+            k_pad_copy(ctx, tmp, rows, k, ld, dst);
+            PCR_CUDA(cudaStreamSynchronize(stream));
+            cudaFree(tmp);
+        }
+    }
+    void get_matrix(const double *src, i64 rows, double *h) {
+        if (rows == 0) return;
+        if (ld == k) {
+            PCR_CUDA(cudaMemcpyAsync(h, src, sizeof(double) * (size_t)rows * k, cudaMemcpyDeviceToHost, stream));
+            PCR_CUDA(cudaStreamSynchronize(stream));
+        } else {
+            double *tmp = nullptr;
+            PCR_CUDA(cudaMalloc(&tmp, sizeof(double) * (size_t)rows * k));
+            k_unpad_copy(ctx, src, rows, k, ld, tmp);
+            PCR_CUDA(cudaMemcpyAsync(h, tmp, sizeof(double) * (size_t)rows * k, cudaMemcpyDeviceToHost, stream));
+            PCR_CUDA(cudaStreamSynchronize(stream));
+            cudaFree(tmp);
+        }
+    }
+    void set_factors(const double *Uh, const double *Vh) {
+        bind();
+        PCR_REQUIRE(has_train, "load the training set first");
+        put_matrix(Uh, d1, U); put_matrix(Vh, d2, V);
+        sync();
+        has_factors = true; scores_valid = false; meta_valid = false;
+    }
+    void get_factors(double *Uh, double *Vh) {
+        bind();
+        PCR_REQUIRE(has_factors, "no factors set");
+        if (Uh) get_matrix(U, d1, Uh);
+        if (Vh) get_matrix(V, d2, Vh);
+        sync();
+    }
+
+    // ------------------------------------------------------------------ small helpers
+    void read_slots(int n) {
+        PCR_CUDA(cudaMemcpyAsync(h_slots, slots, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+        PCR_CUDA(cudaStreamSynchronize(stream));
+    }
+    int read_counter(int which) {
+        PCR_CUDA(cudaMemcpyAsync(h_counters, us.counters, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream));
+        PCR_CUDA(cudaStreamSynchronize(stream));
+        return h_counters[which];
+    }
+    void zero_counters() { PCR_CUDA(cudaMemsetAsync(us.counters, 0, sizeof(int) * 4, stream)); }
+    void allreduce(double *buf, size_t n) {
+        if (world <= 1) return;
+        prof.begin("nccl_allreduce", stream, 0.0);
+        int r = g_nccl.AllReduce(buf, buf, n, PCR_NCCL_FLOAT64, PCR_NCCL_SUM, comm, stream);
+        prof.end(stream);
+        if (r != 0) throw Error(PRIMALCR_ENCCL, std::string("ncclAllReduce failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    }
+    double pass_bytes(i64 n, i64 prows) const { return (double)n * (8.0 * k + 12.0) + 8.0 * k * (double)prows; }
+
+    // scores of all training ratings under (Um, Vm): comp_m_new pcrpp.cpp:17-35
+    void scores(const double *Um, const double *Vm, double *out, const uint8_t *active) {
+        k_dots(ctx, Um, X.user, Vm, X.item, X.nnz, ld, active, out, active ? 0.0 : pass_bytes(X.nnz, d1));
+    }
+    // get_sorted_mm + window pointers for every (active) user
+    void prepare(const double *sc, const uint8_t *active) {
+        k_sort_users(ctx, 0, X.cls_users[0], X.n_cls[0], active, X.row_ptr, sc, X.level, meta);
+        k_sort_users(ctx, 1, X.cls_users[1], X.n_cls[1], active, X.row_ptr, sc, X.level, meta);
+        if (X.n_cls[2] > 0) {
+            k_heavy_sort(ctx, pool, &cub_tmp, &cub_tmp_bytes, sc, iota, meta.s, meta.pos, X.nnz, X.n_cls[2], X.heavy_begin, X.heavy_end);
+            k_gather_level(ctx, X.cls_users[2], X.n_cls[2], nullptr, X.row_ptr, X.level, meta);
+        }
+        for (int q = 0; q < 3; ++q)
+            k_windows(ctx, q, X.cls_users[q], X.n_cls[q], q == 2 ? nullptr : active, X.row_ptr, meta, T, X.heavy_off, h_cnt);
+        meta_valid = true;
+    }
+    void sweep_coeff(int mode, const uint8_t *active, const double *bsrc) {
+        for (int q = 0; q < 3; ++q)
+            k_sweep_coeff(ctx, q, mode, X.cls_users[q], X.n_cls[q], active, X.row_ptr, meta, bsrc, cbuf, T, X.heavy_off, h_v, h_p1, h_acc);
+    }
+    void sweep_obj(const uint8_t *active) {
+        for (int q = 0; q < 3; ++q)
+            k_sweep_obj(ctx, q, X.cls_users[q], X.n_cls[q], active, X.row_ptr, meta, us.loss, T, X.heavy_off, h_p1, h_p2, h_acc);
+    }
+    // per-user losses of the current scores `sc` into us.loss (both solvers)
+    void user_losses(const double *sc, const uint8_t *active) {
+        if (cfg.solver == 2) sweep_obj(active);
+        else { k_pairs(ctx, 2, X, active, sc, nullptr, nullptr, obj_item); k_pair_obj_users(ctx, X, active, obj_item, us.loss); }
+    }
+    // coefficient c_e (CSR order) into cbuf: mode 0 gradient, mode 1 Hv with b
+    void coeffs(int mode, const uint8_t *active) {
+        if (cfg.solver == 2) sweep_coeff(mode, active, b);
+        else k_pairs(ctx, mode, X, active, m, b, cbuf, nullptr);
+    }
+    // full objective of (Um, Vm) given that us.loss holds the per-user losses:
+    //   sum loss + lambda (||U||^2 + ||V||^2) / 2        pcrpp.cpp:410, pcr.cpp:41
+    double total_objective(const double *Um, const double *Vm) {
+        k_sum(ctx, us.loss, d1, red_partials, slots + 0);
+        k_dot(ctx, Um, Um, d1 * ld, red_partials, slots + 1);
+        k_dot(ctx, Vm, Vm, d2 * ld, red_partials, slots + 2);
+        allreduce(slots, 2);
+        read_slots(3);
+        return h_slots[0] + cfg.lambda * (h_slots[1] + h_slots[2]) / 2.0;
+    }
+    // out = lambda*x + sum over the CSC of cbuf[e] * U[user(e)]    (V-side gradient / Hessian-vector product)
+    void rowsum_items(const double *x, double *out) {
+        const double bytes = pass_bytes(X.nnz, d2);
+        if (world <= 1) {
+            k_rowsum(ctx, cu_seg, cu_start, n_cunits, col_unit_ptr, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
+                     cfg.lambda, x, out, 0, bytes);
+        } else {
+            k_rowsum(ctx, cu_seg, cu_start, n_cunits, col_unit_ptr, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
+                     0.0, nullptr, out, 0, bytes);
+            allreduce(out, (size_t)d2 * ld);
+            k_axpby(ctx, out, 1.0, out, cfg.lambda, x, d2 * ld);
+        }
+    }
+    // out[i] = lambda*x[i] + sum over user i of cbuf[e] * V[item(e)]   (U-side gradient / Hessian-vector product)
+    void rowsum_users(const double *x, double *out, const uint8_t *active, int zero_if_empty) {
+        k_rowsum(ctx, X.un_seg, X.un_start, X.n_units, X.seg_unit_ptr, d1, X.item, nullptr, cbuf, V, ld, active, partial,
+                 cfg.lambda, x, out, zero_if_empty, active ? 0.0 : pass_bytes(X.nnz, d1));
+    }
+
+    void require_ready() {
+        PCR_REQUIRE(has_train && has_factors, "engine needs a training set and factors");
+        bind();
+    }
+    void ensure_scores() { if (!scores_valid) { scores(U, V, m, nullptr); scores_valid = true; meta_valid = false; } }
+    void ensure_meta() { ensure_scores(); if (cfg.solver == 2 && !meta_valid) prepare(m, nullptr); }
+
+    // ------------------------------------------------------------------ stage entry points
+    double objective_current() {   // objective_new(m, U, V) / objective(m, U, V)
+        require_ready(); ensure_meta();
+        user_losses(m, nullptr);
+        return total_objective(U, V);
+    }
+    void grad_V(double *out_dev) { // obtain_g_new / obtain_g
+        require_ready(); ensure_meta();
+        coeffs(0, nullptr);
+        rowsum_items(V, out_dev);
+    }
+    void hv_V(const double *a_dev, double *out_dev) {   // compute_Ha_new / compute_Ha
+        require_ready(); ensure_meta();
+        k_dots(ctx, U, X.user, a_dev, X.item, X.nnz, ld, nullptr, b, pass_bytes(X.nnz, d1));
+        coeffs(1, nullptr);
+        rowsum_items(a_dev, out_dev);
+    }
+
+    // ------------------------------------------------------------------ update_V(_new)
+    double update_V() {
+        require_ready();
+        const i64 vn = d2 * ld;
+        scores(U, V, m, nullptr); scores_valid = true; meta_valid = false;
+        if (cfg.solver == 2) prepare(m, nullptr);
+        coeffs(0, nullptr);
+        rowsum_items(V, g);
+        // prev_obj = objective(m, U, V): m and the sorted state do not change during CG, so evaluate it now
+        user_losses(m, nullptr);
+        const double prev_obj = total_objective(U, V);
+        // ---- solve_delta(_new): pcrpp.cpp:335-358
+        k_fill(ctx, delta, vn, 0.0);
+        k_axpby(ctx, rr, -1.0, g, 0.0, g, vn);
+        k_axpby(ctx, p, 1.0, g, 0.0, g, vn);
+        k_dot(ctx, rr, rr, vn, red_partials, slots + 0);
+        read_slots(1);
+        const double err = std::sqrt(h_slots[0]) * 0.01;
+        int its = 0;
+        for (int it = 1; it <= 10; ++it) {
+            k_dots(ctx, U, X.user, p, X.item, X.nnz, ld, nullptr, b, pass_bytes(X.nnz, d1));
+            coeffs(1, nullptr);
+            rowsum_items(p, Hp);
+            ++its;
+            k_dot(ctx, p, Hp, vn, red_partials, slots + 0);
+            k_dot(ctx, rr, p, vn, red_partials, slots + 1);
+            read_slots(2);
+            const double prod_p_Hp = h_slots[0];
+            const double alpha = -1.0 * h_slots[1] / prod_p_Hp;
+            k_axpby(ctx, delta, 1.0, delta, alpha, p, vn);
+            k_axpby(ctx, rr, 1.0, rr, alpha, Hp, vn);
+            k_dot(ctx, rr, rr, vn, red_partials, slots + 0);
+            k_dot(ctx, rr, Hp, vn, red_partials, slots + 1);
+            read_slots(2);
+            if (std::sqrt(h_slots[0]) < err) break;
+            const double beta = h_slots[1] / prod_p_Hp;
+            k_axpby(ctx, p, -1.0, rr, beta, p, vn);
+        }
+        // ---- line search: pcrpp.cpp:427-441
+        double stepsize = cfg.stepsize, now_obj = prev_obj;
+        int trials = 0, accepted = 0;
+        for (int iter = 0; iter < 20; ++iter) {
+            k_axpby(ctx, Vnew, 1.0, V, -stepsize, delta, vn);
+            scores(U, Vnew, m, nullptr);
+            if (cfg.solver == 2) prepare(m, nullptr);
+            user_losses(m, nullptr);
+            now_obj = total_objective(U, Vnew);
+            ++trials;
+            if (now_obj < prev_obj) { std::swap(V, Vnew); accepted = 1; break; }
+            stepsize /= 2.0;
+        }
+        // m (and the sorted state) are those of the LAST trial, accepted or not -- as in the reference (:443)
+        scores_valid = accepted != 0;   // if rejected, m belongs to a V that was thrown away
+        counters.v_cg_iters = its; counters.v_ls_trials = trials; counters.v_ls_accepted = accepted;
+        v_accepted = accepted;
+        last_m_is_stale = !accepted;
+        return now_obj;
+    }
+    bool last_m_is_stale = false;
+
+    // ------------------------------------------------------------------ update_U(_new), batched over users
+    double update_U() {
+        require_ready();
+        if (!scores_valid && !last_m_is_stale) { scores(U, V, m, nullptr); scores_valid = true; meta_valid = false; }
+        if (cfg.solver == 2 && !meta_valid) prepare(m, nullptr);
+        // gradient coefficients from m (stale m included, as precompute_ui / obtain_g_u do)
+        coeffs(0, nullptr);
+        // prev_obj: Primal-CR++ takes it from the same sorted state (objective_u_new :785); Primal-CR recomputes
+        // the scores with the current (u_i, V) (compute_mm pcr.cpp:549), which differs only if V's search failed
+        if (cfg.solver == 1 && last_m_is_stale) {
+            k_dots(ctx, U, X.user, V, X.item, X.nnz, ld, nullptr, b, pass_bytes(X.nnz, d1));
+            user_losses(b, nullptr);
+        } else {
+            user_losses(m, nullptr);
+        }
+        rowsum_users(U, us.g, nullptr, 1);
+        zero_counters();
+        k_u_init(ctx, us, U, X.row_ptr, cfg.solver == 1 ? has_pairs : nullptr, d1, ld, cfg.lambda);
+        int n_active = read_counter(0);
+        // ---- solve_delta_u(_new): <= 10 CG iterations, each user leaves when its residual test fires
+        for (int it = 1; it <= 10 && n_active > 0; ++it) {
+            k_dots(ctx, us.p, X.user, V, X.item, X.nnz, ld, us.cg_active, b, 0.0);
+            coeffs(1, us.cg_active);
+            rowsum_users(us.p, us.Hp, us.cg_active, 0);
+            zero_counters();
+            k_u_cg_step(ctx, us, d1, ld);
+            n_active = read_counter(0);
+        }
+        // ---- line search: <= 20 halvings per user; the last trial is kept even if it never decreased (:814)
+        zero_counters();
+        int n_ls = -1;
+        for (int trial = 0; trial < 20; ++trial) {
+            k_u_ls_trial(ctx, us, U, d1, ld, cfg.stepsize, trial == 0);
+            if (trial == 0) { n_ls = read_counter(1); if (n_ls == 0) break; }
+            double *dst = cfg.solver == 2 ? m : b;
+            k_dots(ctx, us.Unew, X.user, V, X.item, X.nnz, ld, us.ls_active, dst, 0.0);
+            if (cfg.solver == 2) prepare(dst, us.ls_active);
+            user_losses(dst, us.ls_active);
+            zero_counters();
+            k_u_ls_check(ctx, us, d1, ld, cfg.lambda, 0);
+            n_ls = read_counter(1);
+            if (n_ls == 0) break;
+        }
+        k_u_commit(ctx, us, U, d1, ld);
+        scores_valid = false; meta_valid = false; last_m_is_stale = false;
+        // now_obj = sum_i obj_u + lambda/2 ||V||^2   (pcrpp.cpp:832-836)
+        k_sum(ctx, us.obj_new, d1, red_partials, slots + 0);
+        k_dot(ctx, V, V, d2 * ld, red_partials, slots + 1);
+        allreduce(slots, 1);
+        PCR_CUDA(cudaMemsetAsync(stats_dev, 0, sizeof(i64) * 8, stream));
+        k_u_stats(ctx, us, X.row_ptr, d1, stats_dev);
+        PCR_CUDA(cudaMemcpyAsync(h_stats, stats_dev, sizeof(i64) * 8, cudaMemcpyDeviceToHost, stream));
+        read_slots(2);
+        counters.u_cg_len_sum = h_stats[3]; counters.u_ls_len_sum = h_stats[4]; counters.u_skipped = h_stats[5];
+        counters.u_cg_iters = h_stats[6]; counters.u_ls_trials = h_stats[7];
+        return h_slots[0] + cfg.lambda / 2.0 * h_slots[1];
+    }
+
+    // U-side stage outputs for tests: g_u (d1 x ld) and obj_u from the current scores
+    void grad_U_stage() {
+        require_ready(); ensure_meta();
+        coeffs(0, nullptr);
+        user_losses(m, nullptr);
+        rowsum_users(U, us.g, nullptr, 1);
+        zero_counters();
+        k_u_init(ctx, us, U, X.row_ptr, cfg.solver == 1 ? has_pairs : nullptr, d1, ld, cfg.lambda);
+    }
+    void hv_U_stage(const double *S_dev, double *out_dev) {
+        require_ready(); ensure_meta();
+        k_dots(ctx, S_dev, X.user, V, X.item, X.nnz, ld, nullptr, b, pass_bytes(X.nnz, d1));
+        coeffs(1, nullptr);
+        rowsum_users(S_dev, out_dev, nullptr, 0);
+    }
+
+    // ------------------------------------------------------------------ compute_pairwise_error_ndcg util.cpp:434-542
+    void eval(int which, double *err, double *ndcg) {
+        require_ready();
+        DevCsr &C = which == 0 ? X : XT;
+        PCR_REQUIRE(which == 0 || has_test, "no test set loaded");
+        double *sc = which == 0 ? b : ev_score_t;
+        k_dots(ctx, U, C.user, V, C.item, C.nnz, ld, nullptr, sc, 0.0);
+        k_eval_pairs(ctx, C, sc, ev_err_item);
+        k_eval_users(ctx, C, sc, ev_err_item, cfg.ndcg_k, ev_a, ev_b, ev_c, ev_d);
+        k_sum(ctx, ev_a, C.d1, red_partials, slots + 0);
+        k_sum(ctx, ev_b, C.d1, red_partials, slots + 1);
+        k_sum(ctx, ev_c, C.d1, red_partials, slots + 2);
+        k_sum(ctx, ev_d, C.d1, red_partials, slots + 3);
+        allreduce(slots, 4);
+        read_slots(4);
+        *err = h_slots[0] / h_slots[2];
+        *ndcg = h_slots[1] / h_slots[3];
+    }
+
+    // ------------------------------------------------------------------ pcrpp() / pcr() driver with the reference's log lines
+    static std::string fmt_g(double v) { char buf[64]; snprintf(buf, sizeof(buf), "%g", v); return buf; }
+    void run(primalcr_log_fn log, void *lctx) {
+        require_ready();
+        auto say = [&](const std::string &s) { if (log && rank == 0) log(s.c_str(), lctx); };
+        say(std::string(cfg.solver == 2 ? "running PrimalCR++ ndcg_k is " : "running PrimalCR ndcg_k is ") + std::to_string(cfg.ndcg_k));
+        say("using " + std::to_string(world) + " B200 GPU(s). ");
+        double now_obj = objective_current();
+        say("Iter 0 time 0 obj " + fmt_g(now_obj));
+        auto do_eval = [&]() {
+            if (!cfg.do_predict) return;
+            double e = 0, n = 0;
+            eval(0, &e, &n);
+            say("(Training) pairwise error is " + fmt_g(e) + " and ndcg is " + fmt_g(n));
+            if (has_test) { eval(1, &e, &n); say("(Testing) pairwise error is " + fmt_g(e) + " and ndcg is " + fmt_g(n)); }
+        };
+        do_eval();
+        double total_time = 0.0;
+        for (int iter = 1; iter <= cfg.maxiter; ++iter) {
+            sync();
+            auto t0 = std::chrono::steady_clock::now();
+            update_V();
+            now_obj = update_U();
+            sync();
+            total_time += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            say("Iter " + std::to_string(iter) + " time " + fmt_g(total_time) + " obj " + fmt_g(now_obj));
+            do_eval();
+        }
+    }
+};
+
+}  // namespace pcr
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+using pcr::Engine;
+
+struct primalcr_engine { Engine *impl; };
+
+#define API_BEGIN try {
+#define API_END                                                                  \
+    } catch (const pcr::Error &e) { pcr::g_last_error = e.what(); return e.code; } \
+    catch (const std::exception &e) { pcr::g_last_error = e.what(); return PRIMALCR_EINTERNAL; } \
+    return PRIMALCR_OK;
+#define CHECK_E(e) if (!(e) || !(e)->impl) { pcr::g_last_error = "null engine"; return PRIMALCR_EARG; }
+
+extern "C" {
+
+const char *primalcr_last_error(void) { return pcr::g_last_error.c_str(); }
+const char *primalcr_version(void) { return "primalcr_b200 0.1.0 (sm_100a)"; }
+
+void primalcr_default_config(primalcr_config *cfg) {
+    if (!cfg) return;
+    cfg->solver = PRIMALCR_SOLVER_PCRPP; cfg->k = 10; cfg->lambda = 5000; cfg->stepsize = 1.0;
+    cfg->maxiter = 10; cfg->ndcg_k = 10; cfg->do_predict = 1; cfg->device = 0;
+}
+
+int primalcr_create(primalcr_engine **out, const primalcr_config *cfg) {
+    if (!out || !cfg) { pcr::g_last_error = "null argument"; return PRIMALCR_EARG; }
+    *out = nullptr;
+    API_BEGIN
+    Engine *e = new Engine(*cfg);
+    primalcr_engine *h = new primalcr_engine; h->impl = e; *out = h;
+    API_END
+}
+
+void primalcr_destroy(primalcr_engine *e) {
+    if (!e) return;
+    try { delete e->impl; } catch (...) {}
+    delete e;
+}
+
+int primalcr_set_levels(primalcr_engine *e, const int64_t *vals, int n) {
+    CHECK_E(e) API_BEGIN
+    PCR_REQUIRE(vals != nullptr, "null level table");
+    std::vector<pcr::i64> v(vals, vals + (n > 0 ? n : 0));
+    e->impl->set_levels(v.data(), n);
+    API_END
+}
+
+int primalcr_set_train_csr(primalcr_engine *e, int64_t d1, int64_t d2, int64_t nnz, const int64_t *row_ptr,
+                           const int32_t *item, const double *rating) {
+    CHECK_E(e) API_BEGIN
+    PCR_REQUIRE(row_ptr && (nnz == 0 || (item && rating)), "null CSR array");
+    e->impl->set_train(d1, d2, nnz, (const pcr::i64 *)row_ptr, item, rating);
+    API_END
+}
+
+int primalcr_set_test_csr(primalcr_engine *e, int64_t nnz, const int64_t *row_ptr, const int32_t *item, const double *rating) {
+    CHECK_E(e) API_BEGIN
+    PCR_REQUIRE(row_ptr && (nnz == 0 || (item && rating)), "null CSR array");
+    e->impl->set_test(nnz, (const pcr::i64 *)row_ptr, item, rating);
+    API_END
+}
+
+int primalcr_set_factors(primalcr_engine *e, const double *U, const double *V) {
+    CHECK_E(e) API_BEGIN
+    PCR_REQUIRE(U && V, "null factor matrix");
+    e->impl->set_factors(U, V);
+    API_END
+}
+
+int primalcr_get_factors(primalcr_engine *e, double *U, double *V) {
+    CHECK_E(e) API_BEGIN
+    e->impl->get_factors(U, V);
+    API_END
+}
+
+int primalcr_nccl_unique_id(void *id128) {
+    API_BEGIN
+    PCR_REQUIRE(id128 != nullptr, "null id buffer");
+    if (!pcr::g_nccl.load()) throw pcr::Error(PRIMALCR_ENCCL, "cannot load libnccl.so.2");
+    pcr_ncclUniqueId id;
+    int r = pcr::g_nccl.GetUniqueId(&id);
+    if (r != 0) throw pcr::Error(PRIMALCR_ENCCL, "ncclGetUniqueId failed");
+    memcpy(id128, &id, sizeof(id));
+    API_END
+}
+
+int primalcr_comm_init(primalcr_engine *e, int rank, int world, const void *id128) {
+    CHECK_E(e) API_BEGIN
+    PCR_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+    Engine *E = e->impl;
+    E->bind();
+    E->rank = rank; E->world = world;
+    if (world > 1) {
+        PCR_REQUIRE(id128 != nullptr, "null unique id");
+        if (!pcr::g_nccl.load()) throw pcr::Error(PRIMALCR_ENCCL, "cannot load libnccl.so.2");
+        pcr_ncclUniqueId id; memcpy(&id, id128, sizeof(id));
+        int r = pcr::g_nccl.CommInitRank(&E->comm, world, id, rank);
+        if (r != 0) throw pcr::Error(PRIMALCR_ENCCL, std::string("ncclCommInitRank failed: ") +
+                                     (pcr::g_nccl.GetErrorString ? pcr::g_nccl.GetErrorString(r) : "?"));
+    }
+    API_END
+}
+
+int primalcr_initial_objective(primalcr_engine *e, double *obj) {
+    CHECK_E(e) API_BEGIN
+    Engine *E = e->impl;
+    E->require_ready();
+    E->scores_valid = false; E->meta_valid = false;
+    const double o = E->objective_current();
+    E->sync();
+    if (obj) *obj = o;
+    API_END
+}
+
+int primalcr_objective(primalcr_engine *e, double *obj) {
+    CHECK_E(e) API_BEGIN
+    const double o = e->impl->objective_current();
+    e->impl->sync();
+    if (obj) *obj = o;
+    API_END
+}
+
+int primalcr_update_V(primalcr_engine *e, double *now_obj) {
+    CHECK_E(e) API_BEGIN
+    const double o = e->impl->update_V();
+    e->impl->sync();
+    if (now_obj) *now_obj = o;
+    API_END
+}
+
+int primalcr_update_U(primalcr_engine *e, double *now_obj) {
+    CHECK_E(e) API_BEGIN
+    const double o = e->impl->update_U();
+    e->impl->sync();
+    if (now_obj) *now_obj = o;
+    API_END
+}
+
+int primalcr_outer_iteration(primalcr_engine *e, double *now_obj) {
+    CHECK_E(e) API_BEGIN
+    e->impl->update_V();
+    const double o = e->impl->update_U();
+    e->impl->sync();
+    if (now_obj) *now_obj = o;
+    API_END
+}
+
+int primalcr_eval(primalcr_engine *e, int which, double *pairwise_error, double *ndcg) {
+    CHECK_E(e) API_BEGIN
+    double a = 0, b = 0;
+    e->impl->eval(which, &a, &b);
+    e->impl->sync();
+    if (pairwise_error) *pairwise_error = a;
+    if (ndcg) *ndcg = b;
+    API_END
+}
+
+int primalcr_run(primalcr_engine *e, primalcr_log_fn log, void *ctx) {
+    CHECK_E(e) API_BEGIN
+    e->impl->run(log, ctx);
+    e->impl->sync();
+    API_END
+}
+
+int primalcr_get_counters(primalcr_engine *e, primalcr_counters *out) {
+    CHECK_E(e) API_BEGIN
+    PCR_REQUIRE(out != nullptr, "null output");
+    *out = e->impl->counters;
+    API_END
+}
+
+// ---- stage entry points ---------------------------------------------------------------------------
+int primalcr_scores(primalcr_engine *e, double *m_out) {
+    CHECK_E(e) API_BEGIN
+    Engine *E = e->impl;
+    E->require_ready();
+    E->scores(E->U, E->V, E->m, nullptr); E->scores_valid = true; E->meta_valid = false; E->last_m_is_stale = false;
+    if (m_out && E->X.nnz) PCR_CUDA(cudaMemcpyAsync(m_out, E->m, sizeof(double) * (size_t)E->X.nnz, cudaMemcpyDeviceToHost, E->stream));
+    E->sync();
+    API_END
+}
+
+int primalcr_set_scores(primalcr_engine *e, const double *m) {
+    CHECK_E(e) API_BEGIN
+    Engine *E = e->impl;
+    E->require_ready();
+    PCR_REQUIRE(m != nullptr || E->X.nnz == 0, "null scores");
+    if (E->X.nnz) PCR_CUDA(cudaMemcpyAsync(E->m, m, sizeof(double) * (size_t)E->X.nnz, cudaMemcpyHostToDevice, E->stream));
+    E->sync();
+    E->scores_valid = true; E->meta_valid = false; E->last_m_is_stale = false;
+    API_END
+}
+
+int primalcr_num_levels(primalcr_engine *e) {
+    if (!e || !e->impl) return PRIMALCR_EARG;
+    return e->impl->T;
+}
+
+int primalcr_sort_segments(primalcr_engine *e, double *sorted, int32_t *perm, int32_t *level, int32_t *ub, int32_t *lb,
+                           int32_t *cnt_lo, int32_t *cnt_hi) {
+    CHECK_E(e) API_BEGIN
+    Engine *E = e->impl;
+    E->require_ready();
+    PCR_REQUIRE(E->cfg.solver == 2, "sorted state exists only for Primal-CR++");
+    E->ensure_scores();
+    E->prepare(E->m, nullptr);
+    E->sync();
+    const size_t n = (size_t)E->X.nnz;
+    if (n) {
+        if (sorted) PCR_CUDA(cudaMemcpy(sorted, E->meta.s, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        if (ub) PCR_CUDA(cudaMemcpy(ub, E->meta.ub, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+        if (lb) PCR_CUDA(cudaMemcpy(lb, E->meta.lb, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+        if (cnt_lo) PCR_CUDA(cudaMemcpy(cnt_lo, E->meta.cnt_lo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+        if (cnt_hi) PCR_CUDA(cudaMemcpy(cnt_hi, E->meta.cnt_hi, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+        if (perm) {
+            std::vector<int32_t> pos(n);
+            PCR_CUDA(cudaMemcpy(pos.data(), E->meta.pos, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+            for (pcr::i64 u = 0; u < E->d1; ++u)
+                for (pcr::i64 q = E->X.h_row_ptr[u]; q < E->X.h_row_ptr[u + 1]; ++q) perm[q] = pos[q] - (int32_t)E->X.h_row_ptr[u];
+        }
+        if (level) {
+            std::vector<uint8_t> lv(n);
+            PCR_CUDA(cudaMemcpy(lv.data(), E->meta.lev, n, cudaMemcpyDeviceToHost));
+            for (size_t q = 0; q < n; ++q) level[q] = lv[q];
+        }
+    }
+    API_END
+}
+
+int primalcr_level_counts(primalcr_engine *e, int32_t *cnt_left, int32_t *cnt_right) {
+    CHECK_E(e) API_BEGIN
+    Engine *E = e->impl;
+    E->require_ready();
+    PCR_REQUIRE(E->cfg.solver == 2, "sorted state exists only for Primal-CR++");
+    E->ensure_meta();
+    const size_t n = (size_t)E->X.nnz * E->T;
+    int32_t *dl = nullptr, *dr = nullptr;
+    PCR_CUDA(cudaMalloc(&dl, sizeof(int32_t) * (n ? n : 1)));
+    PCR_CUDA(cudaMalloc(&dr, sizeof(int32_t) * (n ? n : 1)));
+    pcr::k_level_counts(E->ctx, E->X.row_ptr, E->d1, E->meta, E->T, dl, dr);
+    E->sync();
+    if (n && cnt_left) PCR_CUDA(cudaMemcpy(cnt_left, dl, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    if (n && cnt_right) PCR_CUDA(cudaMemcpy(cnt_right, dr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    cudaFree(dl); cudaFree(dr);
+    API_END
+}
+
+int primalcr_grad_V(primalcr_engine *e, double *g_out) {
+    CHECK_E(e) API_BEGIN
+    Engine *E = e->impl;
+    E->grad_V(E->g);
+    if (g_out) E->get_matrix(E->g, E->d2, g_out);
+    E->sync();
+    API_END
+}
+
+int primalcr_hv_V(primalcr_engine *e, const double *a, double *Ha_out) {
+    CHECK_E(e) API_BEGIN
+    Engine *E = e->impl;
+    E->require_ready();
+    PCR_REQUIRE(a != nullptr, "null direction");
+    E->put_matrix(a, E->d2, E->p);
+    E->hv_V(E->p, E->Hp);
+    if (Ha_out) E->get_matrix(E->Hp, E->d2, Ha_out);
+    E->sync();
+    API_END
+}
+
+int primalcr_grad_U(primalcr_engine *e, double *g_out, double *obj_u_out) {
+    CHECK_E(e) API_BEGIN
+    Engine *E = e->impl;
+    E->grad_U_stage();
+    if (g_out) E->get_matrix(E->us.g, E->d1, g_out);
+    if (obj_u_out && E->d1) PCR_CUDA(cudaMemcpyAsync(obj_u_out, E->us.prev_obj, sizeof(double) * (size_t)E->d1, cudaMemcpyDeviceToHost, E->stream));
+    E->sync();
+    API_END
+}
+
+int primalcr_hv_U(primalcr_engine *e, const double *S, double *HS_out) {
+    CHECK_E(e) API_BEGIN
+    Engine *E = e->impl;
+    E->require_ready();
+    PCR_REQUIRE(S != nullptr, "null direction");
+    E->put_matrix(S, E->d1, E->us.p);
+    E->hv_U_stage(E->us.p, E->us.Hp);
+    if (HS_out) E->get_matrix(E->us.Hp, E->d1, HS_out);
+    E->sync();
+    API_END
+}
+
+// ---- measurement ------------------------------------------------------------------------------------
+void *primalcr_stream(primalcr_engine *e) { return (e && e->impl) ? (void *)e->impl->stream : nullptr; }
+int64_t primalcr_launch_count(primalcr_engine *e) { return (e && e->impl) ? e->impl->prof.launches : -1; }
+int primalcr_profile_enable(primalcr_engine *e, int on) {
+    CHECK_E(e) API_BEGIN
+    e->impl->bind(); e->impl->sync();
+    e->impl->prof.enabled = on != 0;
+    API_END
+}
+int primalcr_profile_reset(primalcr_engine *e) {
+    CHECK_E(e) API_BEGIN
+    e->impl->bind(); e->impl->sync();
+    e->impl->prof.reset();
+    API_END
+}
+int primalcr_profile_count(primalcr_engine *e) { return (e && e->impl) ? (int)e->impl->prof.acc.size() : -1; }
+int primalcr_profile_get(primalcr_engine *e, int idx, const char **name, double *total_ms, int64_t *launches, double *bytes) {
+    CHECK_E(e) API_BEGIN
+    Engine *E = e->impl;
+    E->bind(); E->sync();
+    PCR_REQUIRE(idx >= 0 && idx < (int)E->prof.acc.size(), "profile index out of range");
+    const auto &a = E->prof.acc[idx];
+    if (name) *name = a.name.c_str();
+    if (total_ms) *total_ms = a.ms;
+    if (launches) *launches = a.launches;
+    if (bytes) *bytes = a.bytes;
+    API_END
+}
+int64_t primalcr_device_bytes(primalcr_engine *e) { return (e && e->impl) ? e->impl->pool.bytes : -1; }
+
+// ---- host utilities -----------------------------------------------------------------------------------
+void primalcr_reference_init(double *out, int64_t n, int64_t k) {
+    // initial() util.cpp:80-93: a default-constructed std::default_random_engine per call
+    std::default_random_engine generator;
+    std::normal_distribution<double> distribution(0.0, 1.0);
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t j = 0; j < k; ++j) out[i * k + j] = distribution(generator);
+}
+
+}  // extern "C"

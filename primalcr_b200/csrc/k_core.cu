@@ -1,0 +1,833 @@
+// k_core.cu -- the Primal-CR++ hot path as hand-written sm_100a kernels.
+//
+//   dots        K1  comp_m_new pcrpp.cpp:17-35, b = U_i . a[p] pcrpp.cpp:266-271, b = s . V[p] :592-594,
+//                   compute_mm_old :728-744          (score gather, 16-byte vector loads, shuffle reduce)
+//   sort        K2  get_sorted_mm pcrpp.cpp:52-83    (per-user bitonic sort in shared memory)
+//   windows     K3  the two sweep pointers + integer level counters pcrpp.cpp:214-229
+//   sweep_*     K3  c_j of obtain_g_new :230-238 / compute_Ha_new :310-318 / obtain_g_u_new :527-535 /
+//                   obtain_Hs_new :613-621 and the objective :392-407, :556-571 as per-level prefix scans
+//   rowsum      K4  G[p,:] += c * U_i  pcrpp.cpp:240-243, :323-327 (item-major over the CSC, no atomics) and
+//                   g += c * V[p] :536, :622 (user-major over the CSR)
+//   u_*         K6  per-user truncated Newton-CG bookkeeping update_u_new :779-815, solve_delta_u_new :628-647
+//   vec         K5  CG vector algebra of solve_delta_new :335-358
+#include "kernels.h"
+#include <math_constants.h>
+
+namespace pcr {
+
+#define FULL 0xffffffffu
+
+#define LAUNCH(ctx, name, bytes, kernel, grid, block, smem, ...)                         \
+    do {                                                                                 \
+        (ctx).prof->begin(name, (ctx).stream, (double)(bytes));                          \
+        kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);                  \
+        (ctx).prof->end((ctx).stream);                                                   \
+        PCR_CUDA(cudaGetLastError());                                                    \
+    } while (0)
+
+static inline unsigned grid_for(i64 work_items, int per_block, int max_blocks) {
+    i64 b = (work_items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (unsigned)b;
+}
+
+// ------------------------------------------------------------------ block primitives
+
+// a[0..n) -> exclusive prefix sums in place, a[n] = total.  Fixed summation tree => deterministic.
+// All threads call; caller synchronises before; ends with __syncthreads().
+template <typename T, int THREADS>
+__device__ __forceinline__ void block_excl_scan(T *a, int n, T *wsum /* [THREADS/32 + 1] shared */) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = (n + THREADS - 1) / THREADS;
+    int lo = tid * chunk; if (lo > n) lo = n;
+    int hi = lo + chunk;  if (hi > n) hi = n;
+    T local = 0;
+    for (int q = lo; q < hi; ++q) local += a[q];
+    T incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        T w = lane < THREADS / 32 ? wsum[lane] : (T)0;
+        T wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; }
+        if (lane < THREADS / 32) wsum[lane] = wi - w;
+        if (lane == 31) wsum[THREADS / 32] = wi;
+    }
+    __syncthreads();
+    T run = wsum[warp] + (incl - local);
+    for (int q = lo; q < hi; ++q) { T v = a[q]; a[q] = run; run += v; }
+    if (tid == 0) a[n] = wsum[THREADS / 32];
+    __syncthreads();
+}
+
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double *wsum /* [THREADS/32] shared */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    __syncthreads();
+    if (lane == 0) wsum[warp] = v;
+    __syncthreads();
+    double r = 0;
+    if (warp == 0) {
+        r = lane < THREADS / 32 ? wsum[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
+    }
+    return r;   // valid in warp 0
+}
+
+// ------------------------------------------------------------------ K1: dots
+
+template <int G>
+__global__ void __launch_bounds__(256) dots_kernel(const double *__restrict__ P, const int32_t *__restrict__ prow,
+                                                   const double *__restrict__ Q, const int32_t *__restrict__ qrow,
+                                                   i64 n, int nch, int ld, const uint8_t *__restrict__ active,
+                                                   double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int lg = lane % G;
+    const int per_warp = 32 / G;
+    const i64 warp_global = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * 256) >> 5;
+    for (i64 base = warp_global * per_warp; base < n; base += nwarps * per_warp) {
+        const i64 e = base + lane / G;
+        bool doit = e < n;
+        int pr = 0, qr = 0;
+        if (doit) { pr = prow[e]; qr = qrow[e]; if (active && !active[pr]) doit = false; }
+        double ax = 0.0, ay = 0.0;
+        if (doit) {
+            const double2 *p2 = reinterpret_cast<const double2 *>(P + (size_t)pr * ld);
+            const double2 *q2 = reinterpret_cast<const double2 *>(Q + (size_t)qr * ld);
+#pragma unroll 4
+            for (int c = lg; c < nch; c += G) {
+                const double2 a = __ldg(p2 + c);
+                const double2 b = __ldg(q2 + c);
+                ax = fma(a.x, b.x, ax);
+                ay = fma(a.y, b.y, ay);
+            }
+        }
+        double s = ax + ay;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if (doit && lg == 0) out[e] = s;
+    }
+}
+
+void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const int32_t *qrow, i64 n, int ld,
+            const uint8_t *active, double *out, double bytes) {
+    if (n <= 0) return;
+    const int nch = ld / 2;
+    if (nch <= 4) {
+        LAUNCH(c, "dots", bytes, dots_kernel<4>, grid_for(n, 256 / 4, c.sms * 8), 256, 0, P, prow, Q, qrow, n, nch, ld, active, out);
+    } else {
+        LAUNCH(c, "dots", bytes, dots_kernel<8>, grid_for(n, 256 / 8, c.sms * 8), 256, 0, P, prow, Q, qrow, n, nch, ld, active, out);
+    }
+}
+
+// ------------------------------------------------------------------ K4: segmented weighted row sums
+
+template <int NCH>
+__global__ void __launch_bounds__(256) rowsum_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
+                                                     i64 n_units, const int32_t *__restrict__ ridx,
+                                                     const int32_t *__restrict__ widx, const double *__restrict__ w,
+                                                     const double *__restrict__ M, int ld, int nch,
+                                                     const uint8_t *__restrict__ active, double *__restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp_global = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * 256) >> 5;
+    for (i64 u = warp_global; u < n_units; u += nwarps) {
+        const int seg = un_seg[u];
+        if (active && !active[seg]) continue;           // warp-uniform
+        const i64 b = un_start[u], e = un_start[u + 1];
+        double2 acc[NCH];
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) acc[q] = make_double2(0.0, 0.0);
+        for (i64 base = b; base < e; base += 32) {
+            const i64 me = base + lane;
+            int ri = 0; double wi = 0.0;
+            if (me < e) { ri = ridx[me]; wi = widx ? w[widx[me]] : w[me]; }
+            const int cnt = (e - base) < 32 ? (int)(e - base) : 32;
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+                const int r = __shfl_sync(FULL, ri, j);
+                const double ww = __shfl_sync(FULL, wi, j);
+                const double2 *row = reinterpret_cast<const double2 *>(M + (size_t)r * ld);
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) {
+                    const int ci = lane + 32 * q;
+                    if (ci < nch) {
+                        const double2 x = __ldg(row + ci);
+                        acc[q].x = fma(ww, x.x, acc[q].x);
+                        acc[q].y = fma(ww, x.y, acc[q].y);
+                    }
+                }
+            }
+        }
+        double2 *o = reinterpret_cast<double2 *>(partial + (size_t)u * ld);
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) { const int ci = lane + 32 * q; if (ci < nch) o[ci] = acc[q]; }
+    }
+}
+
+// out[seg] = lambda*x[seg] + partial[first unit] + partial[second unit] + ...   (fixed order)
+__global__ void __launch_bounds__(256) rowsum_finalize_kernel(const i64 *__restrict__ seg_unit_ptr, i64 n_seg,
+                                                              const double *__restrict__ partial, int ld,
+                                                              const uint8_t *__restrict__ active, double lambda,
+                                                              const double *__restrict__ x, double *__restrict__ out,
+                                                              int zero_if_empty) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp_global = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * 256) >> 5;
+    for (i64 seg = warp_global; seg < n_seg; seg += nwarps) {
+        if (active && !active[seg]) continue;
+        const i64 u0 = seg_unit_ptr[seg], u1 = seg_unit_ptr[seg + 1];
+        for (int cidx = lane; cidx < ld; cidx += 32) {
+            double v = (x != nullptr && !(zero_if_empty && u0 == u1)) ? lambda * x[(size_t)seg * ld + cidx] : 0.0;
+            for (i64 u = u0; u < u1; ++u) v += partial[(size_t)u * ld + cidx];
+            out[(size_t)seg * ld + cidx] = v;
+        }
+    }
+}
+
+void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, const i64 *seg_unit_ptr, i64 n_seg,
+              const int32_t *ridx, const int32_t *widx, const double *w, const double *M, int ld,
+              const uint8_t *active, double *partial, double lambda, const double *x, double *out,
+              int zero_if_empty, double bytes) {
+    const int nch = ld / 2;
+    const int NCH = (nch + 31) / 32;
+    PCR_REQUIRE(NCH <= 4, "rank too large for rowsum kernel (k <= 256)");
+    if (n_units > 0) {
+        const unsigned grid = grid_for(n_units, 8, c.sms * 8);
+        switch (NCH) {
+            case 1: LAUNCH(c, "rowsum", bytes, rowsum_kernel<1>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+            case 2: LAUNCH(c, "rowsum", bytes, rowsum_kernel<2>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+            case 3: LAUNCH(c, "rowsum", bytes, rowsum_kernel<3>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+            default: LAUNCH(c, "rowsum", bytes, rowsum_kernel<4>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+        }
+    }
+    if (n_seg > 0)
+        LAUNCH(c, "rowsum_finalize", 0.0, rowsum_finalize_kernel, grid_for(n_seg, 8, c.sms * 8), 256, 0, seg_unit_ptr, n_seg,
+               partial, ld, active, lambda, x, out, zero_if_empty);
+}
+
+// ------------------------------------------------------------------ K2: per-user bitonic sort (classes S and L)
+
+template <int THREADS, int CAP>
+__global__ void __launch_bounds__(THREADS) sort_users_kernel(const int32_t *__restrict__ users, int n_users,
+                                                             const uint8_t *__restrict__ active,
+                                                             const i64 *__restrict__ row_ptr,
+                                                             const double *__restrict__ m,
+                                                             const uint8_t *__restrict__ level,
+                                                             double *__restrict__ s_out, int32_t *__restrict__ pos_out,
+                                                             uint8_t *__restrict__ lev_out) {
+    __shared__ double keys[CAP];
+    __shared__ uint16_t idx[CAP];
+    const int u = users[blockIdx.x];
+    if (active && !active[u]) return;
+    const i64 start = row_ptr[u];
+    const int n = (int)(row_ptr[u + 1] - start);
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    const int tid = threadIdx.x;
+    for (int j = tid; j < np2; j += THREADS) {
+        keys[j] = j < n ? m[start + j] : CUDART_INF;
+        idx[j] = (uint16_t)j;
+    }
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (np2 >> 1); t += THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const bool asc = (i & k) == 0;
+                const double ki = keys[i], kp = keys[p];
+                const uint16_t ii = idx[i], ip = idx[p];
+                const bool gt = (ki > kp) || (ki == kp && ii > ip);
+                if (gt == asc) { keys[i] = kp; keys[p] = ki; idx[i] = ip; idx[p] = ii; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = tid; j < n; j += THREADS) {
+        const int src = idx[j];
+        s_out[start + j] = keys[j];
+        pos_out[start + j] = (int32_t)(start + src);
+        lev_out[start + j] = level[start + src];
+    }
+}
+
+void k_sort_users(Ctx &c, int cls, const int32_t *users, int n_users, const uint8_t *active, const i64 *row_ptr,
+                  const double *m, const uint8_t *level, SortedMeta &meta) {
+    if (n_users <= 0) return;
+    if (cls == 0)
+        LAUNCH(c, "sort_users_S", 0.0, (sort_users_kernel<256, S_CAP>), n_users, 256, 0, users, n_users, active, row_ptr, m, level, meta.s, meta.pos, meta.lev);
+    else
+        LAUNCH(c, "sort_users_L", 0.0, (sort_users_kernel<1024, L_CAP>), n_users, 1024, 0, users, n_users, active, row_ptr, m, level, meta.s, meta.pos, meta.lev);
+}
+
+// heavy users: CUB wrote s and pos; fetch the levels
+__global__ void __launch_bounds__(256) gather_level_kernel(const int32_t *__restrict__ users, int n_users,
+                                                           const uint8_t *__restrict__ active,
+                                                           const i64 *__restrict__ row_ptr,
+                                                           const uint8_t *__restrict__ level,
+                                                           const int32_t *__restrict__ pos, uint8_t *__restrict__ lev_out) {
+    const int u = users[blockIdx.x];
+    if (active && !active[u]) return;
+    const i64 start = row_ptr[u], end = row_ptr[u + 1];
+    for (i64 j = start + threadIdx.x; j < end; j += 256) lev_out[j] = level[pos[j]];
+}
+
+void k_gather_level(Ctx &c, const int32_t *users, int n_users, const uint8_t *active, const i64 *row_ptr,
+                    const uint8_t *level, SortedMeta &meta) {
+    if (n_users <= 0) return;
+    LAUNCH(c, "gather_level", 0.0, gather_level_kernel, n_users, 256, 0, users, n_users, active, row_ptr, level, meta.pos, meta.lev);
+}
+
+// ------------------------------------------------------------------ K3: window pointers + integer level counters
+//
+// ub_j = #{q : s_q <= fl(s_j + 1.0)}  (now_left  after the first  while loop, pcrpp.cpp:218-223)
+// lb_j = #{q : s_q <  fl(s_j - 1.0)}  (now_right after the second while loop, pcrpp.cpp:224-229)
+// cnt_hi_j = sum_{t > l_j} count_left[t]  = #{q < ub_j : l_q > l_j}
+// cnt_lo_j = sum_{t < l_j} count_right[t] = #{q >= lb_j : l_q < l_j}
+// computed with one exclusive scan per level threshold t: C(x) = #{q < x : l_q >= t}.
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) windows_kernel(const int32_t *__restrict__ users, int n_users,
+                                                          const uint8_t *__restrict__ active,
+                                                          const i64 *__restrict__ row_ptr,
+                                                          const double *__restrict__ s_g, const uint8_t *__restrict__ lev_g,
+                                                          int32_t *__restrict__ ub_g, int32_t *__restrict__ lb_g,
+                                                          int32_t *__restrict__ lo_g, int32_t *__restrict__ hi_g,
+                                                          int T, int smem_cap, const i64 *__restrict__ heavy_off,
+                                                          int32_t *__restrict__ g_cnt) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ int wsum[THREADS / 32 + 1];
+    __shared__ unsigned s_mask;
+    const int u = users[blockIdx.x];
+    if (active && !active[u]) return;
+    const i64 start = row_ptr[u];
+    const int n = (int)(row_ptr[u + 1] - start);
+    const int tid = threadIdx.x;
+    const double *keys;
+    int *cnt;
+    if (tid == 0) s_mask = 0u;
+    if (n <= smem_cap) {
+        double *k = reinterpret_cast<double *>(smraw);
+        for (int j = tid; j < n; j += THREADS) k[j] = s_g[start + j];
+        keys = k;
+        cnt = reinterpret_cast<int *>(k + smem_cap);
+    } else {
+        keys = s_g + start;
+        cnt = g_cnt + heavy_off[u];
+    }
+    __syncthreads();
+    unsigned mymask = 0u;
+    for (int j = tid; j < n; j += THREADS) {
+        const double sj = keys[j];
+        const double hi = __dadd_rn(sj, 1.0), lo = __dadd_rn(sj, -1.0);
+        int a = j + 1, b = n;            // first q in [j+1, n] with keys[q] > hi
+        while (a < b) { const int mid = (a + b) >> 1; if (keys[mid] <= hi) a = mid + 1; else b = mid; }
+        const int ub = a;
+        a = 0; b = j;                    // first q in [0, j] with keys[q] >= lo
+        while (a < b) { const int mid = (a + b) >> 1; if (keys[mid] < lo) a = mid + 1; else b = mid; }
+        const int lb = a;
+        ub_g[start + j] = ub; lb_g[start + j] = lb;
+        lo_g[start + j] = 0;  hi_g[start + j] = 0;
+        mymask |= 1u << lev_g[start + j];
+    }
+    mymask = __reduce_or_sync(FULL, mymask);
+    if ((tid & 31) == 0 && mymask) atomicOr(&s_mask, mymask);
+    __syncthreads();
+    const unsigned mask = s_mask;
+    for (int t = 1; t < T; ++t) {
+        if (!(mask & ((1u << t) | (1u << (t - 1))))) continue;     // block-uniform
+        for (int j = tid; j < n; j += THREADS) cnt[j] = lev_g[start + j] >= t ? 1 : 0;
+        __syncthreads();
+        block_excl_scan<int, THREADS>(cnt, n, wsum);
+        const int total = cnt[n];
+        for (int j = tid; j < n; j += THREADS) {
+            const int l = lev_g[start + j];
+            if (l + 1 == t) hi_g[start + j] = cnt[ub_g[start + j]];
+            if (l == t) { const int lb = lb_g[start + j]; lo_g[start + j] = (n - lb) - (total - cnt[lb]); }
+        }
+        __syncthreads();
+    }
+}
+
+void k_windows(Ctx &c, int cls, const int32_t *users, int n_users, const uint8_t *active, const i64 *row_ptr,
+               SortedMeta &meta, int T, const i64 *heavy_off, int32_t *g_cnt) {
+    if (n_users <= 0) return;
+    if (cls == 0) {
+        const size_t sm = (size_t)S_CAP * 8 + ((size_t)S_CAP + 1) * 4;
+        LAUNCH(c, "windows_S", 0.0, windows_kernel<256>, n_users, 256, sm, users, n_users, active, row_ptr, meta.s, meta.lev,
+               meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, T, S_CAP, heavy_off, g_cnt);
+    } else if (cls == 1) {
+        const size_t sm = (size_t)L_CAP * 8 + ((size_t)L_CAP + 1) * 4;
+        PCR_CUDA(cudaFuncSetAttribute(windows_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        LAUNCH(c, "windows_L", 0.0, windows_kernel<1024>, n_users, 1024, sm, users, n_users, active, row_ptr, meta.s, meta.lev,
+               meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, T, L_CAP, heavy_off, g_cnt);
+    } else {
+        LAUNCH(c, "windows_H", 0.0, windows_kernel<1024>, n_users, 1024, 0, users, n_users, active, row_ptr, meta.s, meta.lev,
+               meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, T, 0, heavy_off, g_cnt);
+    }
+}
+
+// test entry point: the per-level counters themselves, by direct counting from ub / lb
+__global__ void __launch_bounds__(128) level_counts_kernel(const i64 *__restrict__ row_ptr, i64 d1,
+                                                           const uint8_t *__restrict__ lev, const int32_t *__restrict__ ub,
+                                                           const int32_t *__restrict__ lb, int T,
+                                                           int32_t *__restrict__ cntL, int32_t *__restrict__ cntR) {
+    const i64 u = blockIdx.x;
+    if (u >= d1) return;
+    const i64 start = row_ptr[u];
+    const int n = (int)(row_ptr[u + 1] - start);
+    for (int j = threadIdx.x; j < n; j += 128) {
+        int cl[MAX_LEVELS], cr[MAX_LEVELS];
+        for (int t = 0; t < T; ++t) { cl[t] = 0; cr[t] = 0; }
+        const int ubj = ub[start + j], lbj = lb[start + j];
+        for (int q = 0; q < n; ++q) {
+            const int l = lev[start + q];
+            if (q < ubj) cl[l]++;
+            if (q >= lbj) cr[l]++;
+        }
+        for (int t = 0; t < T; ++t) { cntL[(start + j) * T + t] = cl[t]; cntR[(start + j) * T + t] = cr[t]; }
+    }
+}
+
+void k_level_counts(Ctx &c, const i64 *row_ptr, i64 d1, const SortedMeta &meta, int T, int32_t *cntL, int32_t *cntR) {
+    if (d1 <= 0) return;
+    LAUNCH(c, "level_counts", 0.0, level_counts_kernel, (unsigned)d1, 128, 0, row_ptr, d1, meta.lev, meta.ub, meta.lb, T, cntL, cntR);
+}
+
+// ------------------------------------------------------------------ K3: sweep coefficients
+//
+// gradient (MODE 0, stream v = s):  c_j = 2 [ cnt_lo (s_j - 1) + cnt_hi (s_j + 1) - acc_j ]
+// Hv       (MODE 1, stream v = b):  c_j = 2 [ (cnt_lo + cnt_hi) b_j - acc_j ]
+// acc_j = sum_{t < l_j} (S_t(n) - S_t(lb_j)) + sum_{t > l_j} S_t(ub_j),  S_t(x) = sum_{q < x, l_q = t} v_q
+
+template <int THREADS, int MODE>
+__global__ void __launch_bounds__(THREADS) sweep_coeff_kernel(const int32_t *__restrict__ users, int n_users,
+                                                              const uint8_t *__restrict__ active,
+                                                              const i64 *__restrict__ row_ptr,
+                                                              const double *__restrict__ s_g, const int32_t *__restrict__ pos_g,
+                                                              const uint8_t *__restrict__ lev_g,
+                                                              const int32_t *__restrict__ ub_g, const int32_t *__restrict__ lb_g,
+                                                              const int32_t *__restrict__ lo_g, const int32_t *__restrict__ hi_g,
+                                                              const double *__restrict__ b_g, double *__restrict__ c_out,
+                                                              int T, int smem_cap, const i64 *__restrict__ heavy_off,
+                                                              double *__restrict__ g_v, double *__restrict__ g_p,
+                                                              double *__restrict__ g_acc) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ double wsum[THREADS / 32 + 1];
+    __shared__ unsigned s_mask;
+    const int u = users[blockIdx.x];
+    if (active && !active[u]) return;
+    const i64 start = row_ptr[u];
+    const int n = (int)(row_ptr[u + 1] - start);
+    const int tid = threadIdx.x;
+    double *v, *P, *acc;
+    if (n <= smem_cap) {
+        v = reinterpret_cast<double *>(smraw); P = v + smem_cap; acc = P + smem_cap + 1;
+    } else {
+        const i64 off = heavy_off[u];
+        v = g_v + off; P = g_p + off; acc = g_acc + off;
+    }
+    if (tid == 0) s_mask = 0u;
+    __syncthreads();
+    unsigned mymask = 0u;
+    for (int j = tid; j < n; j += THREADS) {
+        v[j] = MODE == 0 ? s_g[start + j] : b_g[pos_g[start + j]];
+        acc[j] = 0.0;
+        mymask |= 1u << lev_g[start + j];
+    }
+    mymask = __reduce_or_sync(FULL, mymask);
+    if ((tid & 31) == 0 && mymask) atomicOr(&s_mask, mymask);
+    __syncthreads();
+    const unsigned mask = s_mask;
+    if ((mask & (mask - 1)) != 0) {          // at least two levels present, otherwise every c_j is 0
+        for (int t = 0; t < T; ++t) {
+            if (!(mask & (1u << t))) continue;
+            for (int j = tid; j < n; j += THREADS) P[j] = lev_g[start + j] == t ? v[j] : 0.0;
+            __syncthreads();
+            block_excl_scan<double, THREADS>(P, n, wsum);
+            const double total = P[n];
+            for (int j = tid; j < n; j += THREADS) {
+                const int l = lev_g[start + j];
+                if (l < t) acc[j] += P[ub_g[start + j]];
+                else if (l > t) acc[j] += total - P[lb_g[start + j]];
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = tid; j < n; j += THREADS) {
+        const double lo = (double)lo_g[start + j], hi = (double)hi_g[start + j];
+        double cc;
+        if (MODE == 0) {
+            const double sj = v[j];
+            cc = lo * (sj - 1.0) + hi * (sj + 1.0) - acc[j];
+        } else {
+            cc = (lo + hi) * v[j] - acc[j];
+        }
+        c_out[pos_g[start + j]] = 2.0 * cc;
+    }
+}
+
+void k_sweep_coeff(Ctx &c, int cls, int mode, const int32_t *users, int n_users, const uint8_t *active,
+                   const i64 *row_ptr, const SortedMeta &meta, const double *b, double *c_out, int T,
+                   const i64 *heavy_off, double *g_v, double *g_p, double *g_acc) {
+    if (n_users <= 0) return;
+#define SWEEP_ARGS users, n_users, active, row_ptr, meta.s, meta.pos, meta.lev, meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, b, c_out, T
+    if (cls == 0) {
+        const size_t sm = ((size_t)3 * S_CAP + 1) * 8;
+        if (mode == 0) LAUNCH(c, "sweep_grad_S", 0.0, (sweep_coeff_kernel<256, 0>), n_users, 256, sm, SWEEP_ARGS, S_CAP, heavy_off, g_v, g_p, g_acc);
+        else           LAUNCH(c, "sweep_hv_S",   0.0, (sweep_coeff_kernel<256, 1>), n_users, 256, sm, SWEEP_ARGS, S_CAP, heavy_off, g_v, g_p, g_acc);
+    } else if (cls == 1) {
+        const size_t sm = ((size_t)3 * L_CAP + 1) * 8;
+        PCR_CUDA(cudaFuncSetAttribute(sweep_coeff_kernel<1024, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        PCR_CUDA(cudaFuncSetAttribute(sweep_coeff_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        if (mode == 0) LAUNCH(c, "sweep_grad_L", 0.0, (sweep_coeff_kernel<1024, 0>), n_users, 1024, sm, SWEEP_ARGS, L_CAP, heavy_off, g_v, g_p, g_acc);
+        else           LAUNCH(c, "sweep_hv_L",   0.0, (sweep_coeff_kernel<1024, 1>), n_users, 1024, sm, SWEEP_ARGS, L_CAP, heavy_off, g_v, g_p, g_acc);
+    } else {
+        if (mode == 0) LAUNCH(c, "sweep_grad_H", 0.0, (sweep_coeff_kernel<1024, 0>), n_users, 1024, 0, SWEEP_ARGS, 0, heavy_off, g_v, g_p, g_acc);
+        else           LAUNCH(c, "sweep_hv_H",   0.0, (sweep_coeff_kernel<1024, 1>), n_users, 1024, 0, SWEEP_ARGS, 0, heavy_off, g_v, g_p, g_acc);
+    }
+#undef SWEEP_ARGS
+}
+
+// ------------------------------------------------------------------ K3: objective sweep
+// loss_u = sum_j [ cnt_hi_j s_j^2 - 2 s_j sum_{t>l_j} S1_t(ub_j) + sum_{t>l_j} S2_t(ub_j) ],
+// S1 = prefix of (s-1), S2 = prefix of (s-1)^2 per level   (objective_new pcrpp.cpp:392-407)
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) sweep_obj_kernel(const int32_t *__restrict__ users, int n_users,
+                                                            const uint8_t *__restrict__ active,
+                                                            const i64 *__restrict__ row_ptr,
+                                                            const double *__restrict__ s_g, const uint8_t *__restrict__ lev_g,
+                                                            const int32_t *__restrict__ ub_g, const int32_t *__restrict__ hi_g,
+                                                            double *__restrict__ obj_user, int T, int smem_cap,
+                                                            const i64 *__restrict__ heavy_off, double *__restrict__ g_p1,
+                                                            double *__restrict__ g_p2, double *__restrict__ g_acc) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ double wsum[THREADS / 32 + 1];
+    __shared__ unsigned s_mask;
+    const int u = users[blockIdx.x];
+    if (active && !active[u]) return;
+    const i64 start = row_ptr[u];
+    const int n = (int)(row_ptr[u + 1] - start);
+    const int tid = threadIdx.x;
+    double *P1, *P2, *acc;
+    if (n <= smem_cap) {
+        P1 = reinterpret_cast<double *>(smraw); P2 = P1 + smem_cap + 1; acc = P2 + smem_cap + 1;
+    } else {
+        const i64 off = heavy_off[u];
+        P1 = g_p1 + off; P2 = g_p2 + off; acc = g_acc + off;
+    }
+    if (tid == 0) s_mask = 0u;
+    __syncthreads();
+    unsigned mymask = 0u;
+    for (int j = tid; j < n; j += THREADS) { acc[j] = 0.0; mymask |= 1u << lev_g[start + j]; }
+    mymask = __reduce_or_sync(FULL, mymask);
+    if ((tid & 31) == 0 && mymask) atomicOr(&s_mask, mymask);
+    __syncthreads();
+    const unsigned mask = s_mask;
+    if ((mask & (mask - 1)) != 0) {
+        for (int t = 1; t < T; ++t) {
+            if (!(mask & (1u << t))) continue;
+            if (!(mask & ((1u << t) - 1u))) continue;      // nothing below level t
+            for (int j = tid; j < n; j += THREADS) {
+                const double d = s_g[start + j] - 1.0;
+                const bool on = lev_g[start + j] == t;
+                P1[j] = on ? d : 0.0;
+                P2[j] = on ? d * d : 0.0;
+            }
+            __syncthreads();
+            block_excl_scan<double, THREADS>(P1, n, wsum);
+            block_excl_scan<double, THREADS>(P2, n, wsum);
+            for (int j = tid; j < n; j += THREADS) {
+                if (lev_g[start + j] < t) {
+                    const int ub = ub_g[start + j];
+                    const double sj = s_g[start + j];
+                    acc[j] += P2[ub] - 2.0 * sj * P1[ub];
+                }
+            }
+            __syncthreads();
+        }
+    }
+    double part = 0.0;
+    for (int j = tid; j < n; j += THREADS) {
+        const double sj = s_g[start + j];
+        part += (double)hi_g[start + j] * (sj * sj) + acc[j];
+    }
+    const double tot = block_sum<THREADS>(part, wsum);
+    if (tid == 0) obj_user[u] = tot;
+}
+
+void k_sweep_obj(Ctx &c, int cls, const int32_t *users, int n_users, const uint8_t *active, const i64 *row_ptr,
+                 const SortedMeta &meta, double *obj_user, int T, const i64 *heavy_off, double *g_p1, double *g_p2,
+                 double *g_acc) {
+    if (n_users <= 0) return;
+#define OBJ_ARGS users, n_users, active, row_ptr, meta.s, meta.lev, meta.ub, meta.cnt_hi, obj_user, T
+    if (cls == 0) {
+        const size_t sm = ((size_t)3 * S_CAP + 2) * 8;
+        LAUNCH(c, "sweep_obj_S", 0.0, sweep_obj_kernel<256>, n_users, 256, sm, OBJ_ARGS, S_CAP, heavy_off, g_p1, g_p2, g_acc);
+    } else if (cls == 1) {
+        const size_t sm = ((size_t)3 * L_CAP + 2) * 8;
+        PCR_CUDA(cudaFuncSetAttribute(sweep_obj_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        LAUNCH(c, "sweep_obj_L", 0.0, sweep_obj_kernel<1024>, n_users, 1024, sm, OBJ_ARGS, L_CAP, heavy_off, g_p1, g_p2, g_acc);
+    } else {
+        LAUNCH(c, "sweep_obj_H", 0.0, sweep_obj_kernel<1024>, n_users, 1024, 0, OBJ_ARGS, 0, heavy_off, g_p1, g_p2, g_acc);
+    }
+#undef OBJ_ARGS
+}
+
+// ------------------------------------------------------------------ K5: dense vector helpers
+
+__global__ void fill_kernel(double *x, i64 n, double v) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) x[i] = v;
+}
+__global__ void fill_u8_kernel(uint8_t *x, i64 n, uint8_t v) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) x[i] = v;
+}
+// out may alias x or y (in-place CG updates): no __restrict__ here
+__global__ void axpby_kernel(double *out, double a, const double *x, double b, const double *y, i64 n) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        out[i] = a * x[i] + b * y[i];
+}
+
+static const int RED_BLOCKS = 592;   // 4 x 148
+
+// MODE 0: x.y   1: sum x   2: sum x[i] where mask[i]
+template <int MODE>
+__global__ void __launch_bounds__(256) reduce_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                                                     const uint8_t *__restrict__ mask, i64 n, double *__restrict__ partials) {
+    __shared__ double wsum[8];
+    double acc = 0.0;
+    for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < n; i += (i64)gridDim.x * 256) {
+        if (MODE == 0) acc = fma(x[i], y[i], acc);
+        else if (MODE == 1) acc += x[i];
+        else if (mask[i]) acc += x[i];
+    }
+    const double t = block_sum<256>(acc, wsum);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(256) reduce_final_kernel(const double *__restrict__ partials, int nb, double *__restrict__ slot) {
+    __shared__ double wsum[8];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nb; i += 256) acc += partials[i];
+    const double t = block_sum<256>(acc, wsum);
+    if (threadIdx.x == 0) *slot = t;
+}
+
+void k_fill(Ctx &c, double *x, i64 n, double v) {
+    if (n <= 0) return;
+    LAUNCH(c, "fill", 0.0, fill_kernel, grid_for(n, 1024, c.sms * 8), 256, 0, x, n, v);
+}
+void k_fill_u8(Ctx &c, uint8_t *x, i64 n, uint8_t v) {
+    if (n <= 0) return;
+    LAUNCH(c, "fill_u8", 0.0, fill_u8_kernel, grid_for(n, 1024, c.sms * 8), 256, 0, x, n, v);
+}
+void k_axpby(Ctx &c, double *out, double a, const double *x, double b, const double *y, i64 n) {
+    if (n <= 0) return;
+    LAUNCH(c, "axpby", 24.0 * n, axpby_kernel, grid_for(n, 1024, c.sms * 8), 256, 0, out, a, x, b, y, n);
+}
+void k_dot(Ctx &c, const double *x, const double *y, i64 n, double *partials, double *slot) {
+    LAUNCH(c, "dot", 16.0 * n, reduce_kernel<0>, RED_BLOCKS, 256, 0, x, y, (const uint8_t *)nullptr, n, partials);
+    LAUNCH(c, "reduce_final", 0.0, reduce_final_kernel, 1, 256, 0, partials, RED_BLOCKS, slot);
+}
+void k_sum(Ctx &c, const double *x, i64 n, double *partials, double *slot) {
+    LAUNCH(c, "sum", 8.0 * n, reduce_kernel<1>, RED_BLOCKS, 256, 0, x, (const double *)nullptr, (const uint8_t *)nullptr, n, partials);
+    LAUNCH(c, "reduce_final", 0.0, reduce_final_kernel, 1, 256, 0, partials, RED_BLOCKS, slot);
+}
+void k_sum_active(Ctx &c, const double *x, const uint8_t *mask, i64 n, double *partials, double *slot) {
+    LAUNCH(c, "sum_active", 9.0 * n, reduce_kernel<2>, RED_BLOCKS, 256, 0, x, (const double *)nullptr, mask, n, partials);
+    LAUNCH(c, "reduce_final", 0.0, reduce_final_kernel, 1, 256, 0, partials, RED_BLOCKS, slot);
+}
+
+__global__ void pad_copy_kernel(const double *__restrict__ src, i64 rows, int k, int ld, double *__restrict__ dst) {
+    const i64 total = rows * ld;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+        const i64 r = i / ld; const int cidx = (int)(i - r * ld);
+        dst[i] = cidx < k ? src[r * k + cidx] : 0.0;
+    }
+}
+__global__ void unpad_copy_kernel(const double *__restrict__ src, i64 rows, int k, int ld, double *__restrict__ dst) {
+    const i64 total = rows * k;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (i64)gridDim.x * blockDim.x) {
+        const i64 r = i / k; const int cidx = (int)(i - r * k);
+        dst[i] = src[r * ld + cidx];
+    }
+}
+void k_pad_copy(Ctx &c, const double *src, i64 rows, int k, int ld, double *dst) {
+    if (rows <= 0) return;
+    LAUNCH(c, "pad_copy", 0.0, pad_copy_kernel, grid_for(rows * ld, 1024, c.sms * 8), 256, 0, src, rows, k, ld, dst);
+}
+void k_unpad_copy(Ctx &c, const double *src, i64 rows, int k, int ld, double *dst) {
+    if (rows <= 0) return;
+    LAUNCH(c, "unpad_copy", 0.0, unpad_copy_kernel, grid_for(rows * k, 1024, c.sms * 8), 256, 0, src, rows, k, ld, dst);
+}
+
+// ------------------------------------------------------------------ K6: batched per-user Newton-CG bookkeeping
+// One warp per user; the k-vectors live in [d1 x ld] arrays.  Follows update_u_new pcrpp.cpp:779-815 /
+// update_u pcr.cpp:523-585 and solve_delta_u(_new) pcrpp.cpp:628-647 / pcr.cpp:498-520.
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// after g (d1 x ld) and loss (d1) are known: prev_obj, skip test, CG initial state
+__global__ void __launch_bounds__(256) u_init_kernel(UState s, const double *__restrict__ U, const i64 *__restrict__ row_ptr,
+                                                     const uint8_t *__restrict__ has_pairs, i64 d1, int ld, double lambda) {
+    const int lane = threadIdx.x & 31;
+    const i64 i = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (i >= d1) return;
+    const size_t o = (size_t)i * ld;
+    double gg = 0.0, uu = 0.0;
+    for (int cidx = lane; cidx < ld; cidx += 32) { const double g = s.g[o + cidx], u = U[o + cidx]; gg = fma(g, g, gg); uu = fma(u, u, uu); }
+    gg = warp_sum(gg); uu = warp_sum(uu);
+    const double prev = lambda / 2.0 * uu + s.loss[i];
+    const bool skip = (gg < 0.0001) || (has_pairs != nullptr && !has_pairs[i]);
+    for (int cidx = lane; cidx < ld; cidx += 32) {
+        const double g = s.g[o + cidx];
+        s.delta[o + cidx] = 0.0; s.rr[o + cidx] = -g; s.p[o + cidx] = g;
+        s.Unew[o + cidx] = U[o + cidx];
+    }
+    if (lane == 0) {
+        s.prev_obj[i] = prev; s.obj_new[i] = prev;
+        s.err[i] = sqrt(gg) * 0.01;
+        s.skipped[i] = skip ? 1 : 0; s.cg_active[i] = skip ? 0 : 1; s.ls_active[i] = 0;
+        s.cg_its[i] = 0; s.ls_trials[i] = 0;
+        if (!skip) atomicAdd(&s.counters[0], 1);
+    }
+}
+
+// one CG iteration's scalar/vector updates for users with cg_active (Hp already holds H p)
+__global__ void __launch_bounds__(256) u_cg_step_kernel(UState s, i64 d1, int ld) {
+    const int lane = threadIdx.x & 31;
+    const i64 i = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (i >= d1) return;
+    if (!s.cg_active[i]) return;
+    const size_t o = (size_t)i * ld;
+    double pHp = 0.0, rp = 0.0;
+    for (int cidx = lane; cidx < ld; cidx += 32) {
+        const double p = s.p[o + cidx];
+        pHp = fma(p, s.Hp[o + cidx], pHp); rp = fma(s.rr[o + cidx], p, rp);
+    }
+    pHp = warp_sum(pHp); rp = warp_sum(rp);
+    const double alpha = -1.0 * rp / pHp;
+    double nr = 0.0, rHp = 0.0;
+    for (int cidx = lane; cidx < ld; cidx += 32) {
+        const double p = s.p[o + cidx], hp = s.Hp[o + cidx];
+        s.delta[o + cidx] = s.delta[o + cidx] + p * alpha;
+        const double r = s.rr[o + cidx] + hp * alpha;
+        s.rr[o + cidx] = r;
+        nr = fma(r, r, nr); rHp = fma(r, hp, rHp);
+    }
+    nr = warp_sum(nr); rHp = warp_sum(rHp);
+    const int its = s.cg_its[i] + 1;
+    const bool done = (sqrt(nr) < s.err[i]) || (its >= 10);
+    if (!done) {
+        const double beta = rHp / pHp;
+        for (int cidx = lane; cidx < ld; cidx += 32) s.p[o + cidx] = -s.rr[o + cidx] + s.p[o + cidx] * beta;
+    }
+    if (lane == 0) {
+        s.cg_its[i] = its;
+        if (done) s.cg_active[i] = 0; else atomicAdd(&s.counters[0], 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) u_ls_begin_kernel(UState s, i64 d1, double stepsize0) {
+    const i64 i = (i64)blockIdx.x * 256 + threadIdx.x;
+    if (i >= d1) return;
+    const bool on = !s.skipped[i];
+    s.ls_active[i] = on ? 1 : 0;
+    s.step[i] = stepsize0;
+    if (on) atomicAdd(&s.counters[1], 1);
+}
+
+// ui_new = ui - step * delta for users still searching
+__global__ void __launch_bounds__(256) u_ls_trial_kernel(UState s, const double *__restrict__ U, i64 d1, int ld) {
+    const int lane = threadIdx.x & 31;
+    const i64 i = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (i >= d1) return;
+    if (!s.ls_active[i]) return;
+    const size_t o = (size_t)i * ld;
+    const double st = s.step[i];
+    for (int cidx = lane; cidx < ld; cidx += 32) s.Unew[o + cidx] = U[o + cidx] + s.delta[o + cidx] * (-st);
+}
+
+// loss[i] now holds the trial's loss: accept / halve (pcrpp.cpp:802-812)
+__global__ void __launch_bounds__(256) u_ls_check_kernel(UState s, i64 d1, int ld, double lambda) {
+    const int lane = threadIdx.x & 31;
+    const i64 i = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (i >= d1) return;
+    if (!s.ls_active[i]) return;
+    const size_t o = (size_t)i * ld;
+    double uu = 0.0;
+    for (int cidx = lane; cidx < ld; cidx += 32) { const double u = s.Unew[o + cidx]; uu = fma(u, u, uu); }
+    uu = warp_sum(uu);
+    if (lane == 0) {
+        const double obj = lambda / 2.0 * uu + s.loss[i];
+        s.obj_new[i] = obj;
+        const int tr = s.ls_trials[i] + 1;
+        s.ls_trials[i] = tr;
+        if (obj < s.prev_obj[i] || tr >= 20) s.ls_active[i] = 0;
+        else { s.step[i] = s.step[i] / 2.0; atomicAdd(&s.counters[1], 1); }
+    }
+}
+
+__global__ void u_commit_kernel(UState s, double *__restrict__ U, i64 d1, int ld) {
+    const i64 total = d1 * ld;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        const i64 i = t / ld;
+        if (!s.skipped[i]) U[t] = s.Unew[t];
+    }
+}
+
+__global__ void __launch_bounds__(256) u_stats_kernel(UState s, const i64 *__restrict__ row_ptr, i64 d1, i64 *__restrict__ out8) {
+    i64 a = 0, b = 0, sk = 0, ci = 0, li = 0;
+    for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < d1; i += (i64)gridDim.x * 256) {
+        const i64 len = row_ptr[i + 1] - row_ptr[i];
+        a += len * s.cg_its[i]; b += len * s.ls_trials[i]; sk += s.skipped[i]; ci += s.cg_its[i]; li += s.ls_trials[i];
+    }
+    atomicAdd((unsigned long long *)&out8[3], (unsigned long long)a);
+    atomicAdd((unsigned long long *)&out8[4], (unsigned long long)b);
+    atomicAdd((unsigned long long *)&out8[5], (unsigned long long)sk);
+    atomicAdd((unsigned long long *)&out8[6], (unsigned long long)ci);
+    atomicAdd((unsigned long long *)&out8[7], (unsigned long long)li);
+}
+
+void k_u_init(Ctx &c, UState &s, const double *U, const i64 *row_ptr, const uint8_t *has_pairs, i64 d1, int ld, double lambda) {
+    if (d1 <= 0) return;
+    LAUNCH(c, "u_init", 0.0, u_init_kernel, (unsigned)((d1 + 7) / 8), 256, 0, s, U, row_ptr, has_pairs, d1, ld, lambda);
+}
+void k_u_cg_step(Ctx &c, UState &s, i64 d1, int ld) {
+    if (d1 <= 0) return;
+    LAUNCH(c, "u_cg_step", 0.0, u_cg_step_kernel, (unsigned)((d1 + 7) / 8), 256, 0, s, d1, ld);
+}
+void k_u_ls_begin(Ctx &c, UState &s, i64 d1) { (void)c; (void)s; (void)d1; }
+void k_u_ls_trial(Ctx &c, UState &s, const double *U, i64 d1, int ld, double stepsize0, int first) {
+    if (d1 <= 0) return;
+    if (first) LAUNCH(c, "u_ls_begin", 0.0, u_ls_begin_kernel, (unsigned)((d1 + 255) / 256), 256, 0, s, d1, stepsize0);
+    LAUNCH(c, "u_ls_trial", 0.0, u_ls_trial_kernel, (unsigned)((d1 + 7) / 8), 256, 0, s, U, d1, ld);
+}
+void k_u_ls_check(Ctx &c, UState &s, i64 d1, int ld, double lambda, int last) {
+    (void)last;
+    if (d1 <= 0) return;
+    LAUNCH(c, "u_ls_check", 0.0, u_ls_check_kernel, (unsigned)((d1 + 7) / 8), 256, 0, s, d1, ld, lambda);
+}
+void k_u_commit(Ctx &c, UState &s, double *U, i64 d1, int ld) {
+    if (d1 <= 0) return;
+    LAUNCH(c, "u_commit", 0.0, u_commit_kernel, grid_for(d1 * ld, 1024, c.sms * 8), 256, 0, s, U, d1, ld);
+}
+void k_u_stats(Ctx &c, UState &s, const i64 *row_ptr, i64 d1, i64 *out8) {
+    if (d1 <= 0) return;
+    LAUNCH(c, "u_stats", 0.0, u_stats_kernel, grid_for(d1, 256, c.sms * 4), 256, 0, s, row_ptr, d1, out8);
+}
+
+}  // namespace pcr

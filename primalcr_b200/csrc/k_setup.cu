@@ -1,0 +1,122 @@
+// k_setup.cu -- one-time preprocessing on the device (replaces convert() util.cpp:219-274 and the CSR->CSC
+// transpose of smat_t::load_from_iterator util.h:259-270) plus the heavy-user segmented sort.
+// CUB (shipped with the CUDA toolkit) is used here only for set-up sorts/scans and for users whose rating
+// count exceeds the shared-memory sort classes; the per-iteration hot kernels are in k_core.cu.
+#include "kernels.h"
+#include <cub/cub.cuh>
+
+namespace pcr {
+
+#define LAUNCH(ctx, name, bytes, kernel, grid, block, smem, ...)                         \
+    do {                                                                                 \
+        (ctx).prof->begin(name, (ctx).stream, (double)(bytes));                          \
+        kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);                  \
+        (ctx).prof->end((ctx).stream);                                                   \
+        PCR_CUDA(cudaGetLastError());                                                    \
+    } while (0)
+
+static inline unsigned grid_for(i64 n, int per_block, int max_blocks) {
+    i64 b = (n + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (unsigned)b;
+}
+
+// user_out[e] = the row that contains CSR position e (binary search in row_ptr)
+__global__ void expand_users_kernel(const i64 *__restrict__ row_ptr, i64 d1, i64 nnz, int32_t *__restrict__ out) {
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (i64)gridDim.x * blockDim.x) {
+        i64 a = 0, b = d1;                 // last u with row_ptr[u] <= e
+        while (b - a > 1) { const i64 mid = (a + b) >> 1; if (row_ptr[mid] <= e) a = mid; else b = mid; }
+        out[e] = (int32_t)a;
+    }
+}
+void k_expand_users(Ctx &c, const i64 *row_ptr, i64 d1, i64 nnz, int32_t *user_out) {
+    if (nnz <= 0) return;
+    LAUNCH(c, "expand_users", 0.0, expand_users_kernel, grid_for(nnz, 256, c.sms * 16), 256, 0, row_ptr, d1, nnz, user_out);
+}
+
+// level index of lround(rating) in the ascending table (find_levels pcrpp.cpp:38-49 + remap :182-189)
+__global__ void levels_kernel(const double *__restrict__ rating, i64 nnz, const i64 *__restrict__ table, int T,
+                              uint8_t *__restrict__ out, int *__restrict__ bad) {
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (i64)gridDim.x * blockDim.x) {
+        const i64 v = llround(rating[e]);
+        int k = 0;
+        while (k < T && table[k] != v) ++k;
+        if (k == T) { *bad = 1; k = 0; }
+        out[e] = (uint8_t)k;
+    }
+}
+void k_levels(Ctx &c, const double *rating, i64 nnz, const i64 *table_dev, int T, uint8_t *level_out, int *bad_flag) {
+    if (nnz <= 0) return;
+    LAUNCH(c, "levels", 0.0, levels_kernel, grid_for(nnz, 256, c.sms * 16), 256, 0, rating, nnz, table_dev, T, level_out, bad_flag);
+}
+
+__global__ void iota32_kernel(int32_t *out, i64 n) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) out[i] = (int32_t)i;
+}
+void k_iota32(Ctx &c, int32_t *out, i64 n) {
+    if (n <= 0) return;
+    LAUNCH(c, "iota32", 0.0, iota32_kernel, grid_for(n, 256, c.sms * 16), 256, 0, out, n);
+}
+
+__global__ void hist_kernel(const int32_t *__restrict__ item, i64 nnz, unsigned long long *__restrict__ counts) {
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (i64)gridDim.x * blockDim.x)
+        atomicAdd(&counts[item[e]], 1ull);
+}
+__global__ void gather_i32_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ idx, i64 n, int32_t *__restrict__ out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) out[i] = src[idx[i]];
+}
+
+void k_build_csc(Ctx &c, DevPool &pool, const int32_t *item, const int32_t *user, i64 nnz, i64 d2,
+                 i64 *col_ptr, int32_t *csc2csr, int32_t *csc_user) {
+    PCR_CUDA(cudaMemsetAsync(col_ptr, 0, sizeof(i64) * (size_t)(d2 + 1), c.stream));
+    if (nnz <= 0) return;
+    // histogram -> exclusive scan = col_ptr
+    unsigned long long *counts = nullptr;
+    PCR_CUDA(cudaMalloc(&counts, sizeof(unsigned long long) * (size_t)(d2 + 1)));
+    PCR_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)(d2 + 1), c.stream));
+    LAUNCH(c, "csc_hist", 0.0, hist_kernel, grid_for(nnz, 256, c.sms * 16), 256, 0, item, nnz, counts);
+    void *tmp = nullptr; size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (const i64 *)counts, col_ptr, (int)(d2 + 1), c.stream);
+    PCR_CUDA(cudaMalloc(&tmp, tb > 0 ? tb : 1));
+    c.prof->begin("csc_scan(cub)", c.stream, 0.0);
+    PCR_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, (const i64 *)counts, col_ptr, (int)(d2 + 1), c.stream));
+    c.prof->end(c.stream);
+    PCR_CUDA(cudaStreamSynchronize(c.stream));
+    cudaFree(tmp); cudaFree(counts);
+    // stable radix sort of (item -> CSR position): users stay ascending inside an item
+    int32_t *keys_out = nullptr, *iota = nullptr;
+    PCR_CUDA(cudaMalloc(&keys_out, sizeof(int32_t) * (size_t)nnz));
+    PCR_CUDA(cudaMalloc(&iota, sizeof(int32_t) * (size_t)nnz));
+    k_iota32(c, iota, nnz);
+    int bits = 1;
+    while (bits < 31 && ((i64)1 << bits) < d2) ++bits;
+    tmp = nullptr; tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, item, keys_out, (const int32_t *)iota, csc2csr, nnz, 0, bits, c.stream);
+    PCR_CUDA(cudaMalloc(&tmp, tb > 0 ? tb : 1));
+    c.prof->begin("csc_sort(cub)", c.stream, 0.0);
+    PCR_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, item, keys_out, (const int32_t *)iota, csc2csr, nnz, 0, bits, c.stream));
+    c.prof->end(c.stream);
+    LAUNCH(c, "csc_users", 0.0, gather_i32_kernel, grid_for(nnz, 256, c.sms * 16), 256, 0, user, csc2csr, nnz, csc_user);
+    PCR_CUDA(cudaStreamSynchronize(c.stream));
+    cudaFree(tmp); cudaFree(keys_out); cudaFree(iota);
+    (void)pool;
+}
+
+void k_heavy_sort(Ctx &c, DevPool &pool, void **temp, size_t *temp_bytes, const double *m, const int32_t *iota,
+                  double *s_sorted, int32_t *pos_sorted, i64 nnz, int n_heavy, const i64 *begin, const i64 *end) {
+    if (n_heavy <= 0) return;
+    size_t need = 0;
+    PCR_CUDA(cub::DeviceSegmentedSort::StableSortPairs(nullptr, need, m, s_sorted, iota, pos_sorted, nnz, (i64)n_heavy,
+                                                       begin, end, c.stream));
+    if (need > *temp_bytes) {
+        *temp = pool.alloc<unsigned char>(need);      // grows monotonically; freed with the engine
+        *temp_bytes = need;
+    }
+    c.prof->begin("heavy_sort(cub)", c.stream, 0.0);
+    PCR_CUDA(cub::DeviceSegmentedSort::StableSortPairs(*temp, need, m, s_sorted, iota, pos_sorted, nnz, (i64)n_heavy,
+                                                       begin, end, c.stream));
+    c.prof->end(c.stream);
+}
+
+}  // namespace pcr
