@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- seconds per Primal-CR++ outer iteration (update_V + update_U), k=100, Netflix-shape synthetic.
+
+    python bench.py --gpus N --steps K --warmup W            # our B200 path   (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU implementation
+
+One JSON line on stdout (rank 0).  A "step" is one outer iteration over the whole (sharded) rating set:
+  value  = device-timed seconds per outer iteration with ratings/factors resident in HBM (max over ranks);
+  e2e    = the same metric through the reference-facing call (host CSR + host U,V in, K iterations, host U,V
+           out), host<->device copies and the one-time CSR/CSC preparation inside the timed region;
+  roofline      = dominant kernel's algorithmic bytes / CUDA-event time vs the measured HBM peak;
+  cpu_baseline  = the reference `omp-pmf-train` (oracle/_ref) on a bounded user sample, extrapolated.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sec_per_outer_iter_primalcrpp_k100_netflix_shape"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.ready = threading.Event()
+        self.window = [None, None]      # perf_counter bounds of the timed region
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                     "hw_power_brake": 0x80}
+            self.ready.set()
+            while not self.stop_flag:
+                now = time.perf_counter()
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((now, mhz, r))
+                time.sleep(0.02)
+        except Exception as ex:      # pragma: no cover - NVML missing
+            self.reasons.add("nvml_unavailable:%s" % type(ex).__name__)
+            self.ready.set()
+        self.names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+                      "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
+
+    def summary(self):
+        t0, t1 = self.window
+        inside = [s for s in self.samples if t0 is None or (t0 <= s[0] <= t1)] or self.samples[-1:]
+        for _, _, r in inside:
+            for n, bit in getattr(self, "names", {}).items():
+                if r & bit:
+                    self.reasons.add(n)
+        return {"sm_mhz": float(np.median([s[1] for s in inside])) if inside else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(inside)}
+
+
+# --------------------------------------------------------------------------------------------- workload
+
+def make_workload(args, device):
+    from primalcr_b200.data import synth_dataset
+    t = time.time()
+    ds = synth_dataset(args.workload, scale=args.scale, device=device, test_per_user=0)
+    log("[bench] %s: d1=%d d2=%d nnz=%d (max len %d) generated on %s in %.1fs" % (
+        ds.name, ds.d1, ds.d2, ds.train.nnz, int(ds.train.lens().max()), device, time.time() - t))
+    return ds
+
+
+def reference_init_cached(n, k):
+    from primalcr_b200 import api
+    return api.reference_init(n, k)
+
+
+# --------------------------------------------------------------------------------------------- CPU reference arm
+
+def run_reference_cli(ds_sample, k, lam, iters, threads):
+    """Times the reference's own omp-pmf-train (oracle/_ref) on `ds_sample`; returns per-iteration seconds."""
+    from primalcr_b200.data import write_reference_dir
+    exe = os.path.join(ROOT, "oracle", "_ref", "omp-pmf-train")
+    with tempfile.TemporaryDirectory() as tmp:
+        d = os.path.join(tmp, "data")
+        write_reference_dir(d, ds_sample)
+        cmd = [exe, "-s", "2", "-k", str(k), "-l", str(lam), "-t", str(iters), "-p", "0", "-n", str(threads), d,
+               os.path.join(tmp, "model")]
+        out = subprocess.run(cmd, cwd=tmp, capture_output=True, text=True, check=True).stdout
+    times = [float(m.group(2)) for m in re.finditer(r"^Iter (\d+) time (\S+) obj", out, re.M)]
+    return np.diff(np.array(times)), out       # times[0] is "Iter 0 time 0"
+
+
+def run_oracle_port(ds_sample, k, lam, iters):
+    from oracle import bindings as ob
+    from primalcr_b200 import api
+    R = ds_sample.train
+    X = ob.Csr(R.d1, R.d2, R.row_ptr, R.item.astype(np.int64), R.rating)
+    U = api.reference_init(R.d1, k); V = api.reference_init(R.d2, k)
+    per = []
+    O = ob.oracle()
+    for _ in range(iters):
+        t = time.time()
+        res = O.train(2, X, None, U, V, lam, 1, do_predict=0)
+        per.append(time.time() - t)
+        U, V = res["U"], res["V"]
+    return np.array(per)
+
+
+def cpu_baseline(ds, args, iters, sample_nnz):
+    """Reference CPU time per outer iteration on a bounded user sample, extrapolated linearly in #ratings."""
+    from primalcr_b200.data import Dataset, Ratings
+    rp = ds.train.row_ptr
+    n_users = int(np.searchsorted(rp, min(sample_nnz, ds.train.nnz), side="left"))
+    n_users = max(1, min(n_users, ds.d1))
+    sample = Dataset(ds.train.slice_users(0, n_users), Ratings.empty(n_users, ds.d2), "sample")
+    cores = os.cpu_count() or 1
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "omp-pmf-train"))
+    t = time.time()
+    if have_ref:
+        per, _ = run_reference_cli(sample, args.k, args.lam, iters, cores)
+        kind = "reference"
+    else:
+        per = run_oracle_port(sample, args.k, args.lam, iters)
+        kind, cores = "port", 1
+    factor = ds.train.nnz / max(sample.train.nnz, 1)
+    log("[bench] cpu %s: %d users / %d ratings, per-iter %s s, x%.1f extrapolation, %.1fs total" % (
+        kind, n_users, sample.train.nnz, np.round(per, 3).tolist(), factor, time.time() - t))
+    return {"per_iter_sample_s": per.tolist(), "factor": factor, "kind": kind, "cores": cores,
+            "sample": "first %d users (%d ratings, %.4f of the workload) of the same synthetic set, omp-pmf-train "
+                      "-s 2 -k %d -l %g -p 0 -n %d; seconds per iteration scaled by nnz ratio %.1f" % (
+                          n_users, sample.train.nnz, sample.train.nnz / ds.train.nnz, args.k, args.lam, cores, factor)}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ds = make_workload(args, "cpu" if args.scale <= 0.05 else _gen_device())
+    iters = args.warmup + args.steps
+    cb = cpu_baseline(ds, args, iters, args.ref_sample_nnz)
+    per = np.array(cb["per_iter_sample_s"])[args.warmup:]
+    value = float(per.mean() * cb["factor"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, ds),
+        "cpu_baseline": {"value": value, "unit": "s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]},
+        "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def _gen_device():
+    try:
+        import torch
+        return "cuda" if torch.cuda.is_available() else "cpu"
+    except Exception:
+        return "cpu"
+
+
+def workload_config(args, ds):
+    return {"workload": "%s, %d users x %d items, %d ratings (levels 1-5), Primal-CR++ -s 2 -k %d -l %g, reference init" % (
+                ds.name, ds.d1, ds.d2, ds.train.nnz, args.k, args.lam),
+            "solver": "Primal-CR++", "k": args.k, "lambda": args.lam, "d1": ds.d1, "d2": ds.d2, "nnz": ds.train.nnz,
+            "parallelism": "users sharded over %d GPU(s) by nnz, V replicated, NCCL allreduce of d2 x k sums" % args.gpus,
+            "l2_policy": "working set (>= 9 GB of ratings + factors per pass at full size) exceeds the 126 MB L2; no flush needed"}
+
+
+# --------------------------------------------------------------------------------------------- our arm
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    from primalcr_b200 import api
+    from primalcr_b200.data import shard_bounds
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: primalcr_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    api.lib()                                   # fail loudly if the extension is missing
+
+    ds = make_workload(args, "cuda")
+    torch.cuda.empty_cache()
+    k, lam = args.k, args.lam
+    bounds = shard_bounds(ds.train.row_ptr, world)
+    u0, u1 = int(bounds[rank]), int(bounds[rank + 1])
+    shard = ds.train.slice_users(u0, u1)
+    t = time.time()
+    U_full = reference_init_cached(ds.d1, k)
+    V_host = U_full[:ds.d2].copy() if ds.d2 <= ds.d1 else reference_init_cached(ds.d2, k)
+    U_host = np.ascontiguousarray(U_full[u0:u1]); del U_full
+    log("[bench] rank %d: users [%d,%d) nnz=%d; reference init in %.1fs" % (rank, u0, u1, shard.nnz, time.time() - t))
+    levels = np.arange(1, 6, dtype=np.int64)
+
+    # pinned host copies (the e2e leg copies from these inside its timed region)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_rp, h_it, h_ra = pin(shard.row_ptr.astype(np.int64)), pin(shard.item.astype(np.int32)), pin(shard.rating)
+    h_U, h_V = pin(U_host), pin(V_host)
+
+    uid = None
+    if world > 1:
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(api.Engine.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    def new_engine(maxiter):
+        p = api.Parameter(solver_type=api.PCRPP, k=k, lambda_=lam, maxiter=maxiter, do_predict=0, device=local)
+        e = api.Engine(p)
+        e.set_levels(levels)
+        if world > 1:
+            e.comm_init(rank, world, uid)
+        return e
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---------------- device-resident leg
+    eng = new_engine(args.steps)
+    eng.set_train_raw(shard.d1, shard.d2, shard.nnz, h_rp, h_it, h_ra)
+    eng.set_factors(h_U, h_V)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=torch.device("cuda", local))
+    obj0 = eng.initial_objective()
+    objs = [obj0]
+    for _ in range(args.warmup):
+        objs.append(eng.outer_iteration())
+    eng.profile_enable(True); eng.profile_reset()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local); sampler.start(); sampler.ready.wait(10)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    counters = []
+    barrier()
+    sampler.window[0] = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        objs.append(eng.outer_iteration())
+        counters.append(eng.counters())
+    ev1.record(stream)
+    barrier()
+    sampler.window[1] = time.perf_counter()
+    sampler.stop_flag = True; sampler.join()
+    sec = max_over_ranks(ev0.elapsed_time(ev1) / 1e3) / args.steps
+    launches = eng.launch_count() - launches0
+    prof = eng.profile()
+    eng.profile_enable(False)
+    dev_bytes = eng.device_bytes()
+    eng.close(); del eng
+    torch.cuda.empty_cache()
+
+    # ---------------- end-to-end leg: host buffers in, K iterations, host factors out
+    outU = torch.empty_like(h_U).pin_memory(); outV = torch.empty_like(h_V).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    e2 = new_engine(args.steps)
+    e2.set_train_raw(shard.d1, shard.d2, shard.nnz, h_rp, h_it, h_ra)
+    e2.set_factors(h_U, h_V)
+    e2.run(log=None)
+    e2.get_factors(outU, outV)
+    barrier()
+    e2e_sec = max_over_ranks(time.perf_counter() - t0) / args.steps
+    e2.close()
+    h2d = (h_rp.numel() * 8 + h_it.numel() * 4 + h_ra.numel() * 8 + h_U.numel() * 8 + h_V.numel() * 8) / args.steps
+    d2h = (outU.numel() * 8 + outV.numel() * 8) / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline
+    peak, peak_src = peaks()
+    N, d1 = ds.train.nnz, ds.d1
+    b_pass = N * (8 * k + 12) + 8 * k * d1
+    its = []
+    for c in counters:     # rank 0's counters; the len-weighted means use rank 0's shard
+        tv, lv = c["v_cg_iters"], c["v_ls_trials"]
+        cu = c["u_cg_len_sum"] / max(shard.nnz, 1); lu = c["u_ls_len_sum"] / max(shard.nnz, 1)
+        pi = 3 + 2 * tv + lv + 2 * cu + lu
+        s = 3 + lv + lu
+        its.append(dict(T_V=tv, L_V=lv, c_U=cu, l_U=lu, passes=pi, sorts=s, b_alg=pi * b_pass + s * 32 * N))
+    b_alg = float(np.mean([i["b_alg"] for i in its]))
+    hot = {n: v for n, v in prof.items() if v["bytes"] > 0}
+    top = max(hot, key=lambda n: hot[n]["ms"]) if hot else None
+    roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None}
+    if top:
+        a = hot[top]["bytes"] / (hot[top]["ms"] / 1e3) / 1e9
+        roof.update(kernel=top, achieved=a, frac=a / peak, launches=hot[top]["launches"],
+                    avg_launch_ms=hot[top]["ms"] / hot[top]["launches"],
+                    bytes_per_launch=hot[top]["bytes"] / hot[top]["launches"],
+                    share_of_step=hot[top]["ms"] / 1e3 / (sec * args.steps))
+    roof.update(peak_source=peak_src,
+                iteration={"b_alg_bytes": b_alg, "achieved": b_alg / sec / 1e9 * 1.0, "frac": b_alg / sec / 1e9 / peak / world,
+                           "note": "B_alg = passes*[N(8k+12)+8k*d1] + sorts*32N (SURVEY 8d); frac is per GPU",
+                           "counters": its[-1]})
+    kern = sorted(((v["ms"], n, v["launches"], v["bytes"]) for n, v in prof.items()), reverse=True)
+    roof["kernels"] = [{"name": n, "ms_per_step": ms / args.steps, "launches_per_step": l / args.steps,
+                        "gbs": (b / (ms / 1e3) / 1e9 if b > 0 and ms > 0 else None)} for ms, n, l, b in kern[:12]]
+
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        c = cpu_baseline(ds, args, 2, args.ref_sample_nnz)
+        per = np.array(c["per_iter_sample_s"])
+        cb = {"value": float(per[-1] * c["factor"]), "unit": "s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]}
+
+    line = {
+        "metric": METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, ds),
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "whole pcrpp()-style call (upload CSR+U+V, build CSC, %d iterations, download U+V) / iterations" % args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roof, "cpu_baseline": cb,
+        "objective": objs, "device_bytes": dev_bytes,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="netflix")
+    ap.add_argument("--scale", type=float, default=1.0, help="user/rating subsample factor of the named shape")
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--lam", type=float, default=5000.0)
+    ap.add_argument("--ref-sample-nnz", type=int, default=2_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -189,12 +189,12 @@ def test_training_trajectory(name, k, lam, iters, solver):
     objs = [float(l.split()[-1]) for l in lines if l.startswith("Iter ")]
     assert len(objs) == iters + 1
     for a, b in zip(objs, res["obj"]):
-        assert abs(a - b) <= 2e-6 * abs(b)          # the log line carries 6 significant digits
+        assert abs(a - b) <= 1e-5 * abs(b)          # the log line carries 6 significant digits
     tr = [l for l in lines if l.startswith("(Training)")]
     te = [l for l in lines if l.startswith("(Testing)")]
     assert len(tr) == iters + 1 and len(te) == iters + 1
     for i in range(iters + 1):
-        assert abs(float(tr[i].split()[4]) - res["evals"][i, 0]) < 2e-6 * max(1.0, res["evals"][i, 0])
+        assert abs(float(tr[i].split()[4]) - res["evals"][i, 0]) < 1e-5
         assert abs(float(te[i].split()[-1]) - res["evals"][i, 3]) < NDCG_TOL
     assert rel(Ug, res["U"]) < 1e-7 and rel(Vg, res["V"]) < 1e-7
     # full-precision objective through the stage API

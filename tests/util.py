@@ -43,6 +43,9 @@ def ragged_dataset(seed=3, d2=6000, real_valued=False) -> Dataset:
     tu, ti, tv = [], [], []
     for u in range(d1):
         n = int(rng.integers(0, 13))
+        a, b = int(train.row_ptr[u]), int(train.row_ptr[u + 1])
+        if b > a and len(np.unique(train.rating[a:b])) < 2:
+            n = 0     # no comparable pair => the Newton step sends u_i to ~0: test scores would be rounding noise
         it = rng.choice(d2, size=n, replace=False)
         tu.append(np.full(n, u)); ti.append(it)
         tv.append(rng.integers(1, 6, size=n).astype(np.float64) if not real_valued else np.round(rng.standard_normal(n), 2))
