@@ -122,9 +122,9 @@ void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const
     if (n <= 0) return;
     const int nch = ld / 2;
     if (nch <= 4) {
-        LAUNCH(c, "dots", bytes, dots_kernel<4>, grid_for(n, 256 / 4, c.sms * 8), 256, 0, P, prow, Q, qrow, n, nch, ld, active, out);
+        LAUNCH(c, active ? "dots_active" : "dots", bytes, dots_kernel<4>, grid_for(n, 256 / 4, c.sms * 8), 256, 0, P, prow, Q, qrow, n, nch, ld, active, out);
     } else {
-        LAUNCH(c, "dots", bytes, dots_kernel<8>, grid_for(n, 256 / 8, c.sms * 8), 256, 0, P, prow, Q, qrow, n, nch, ld, active, out);
+        LAUNCH(c, active ? "dots_active" : "dots", bytes, dots_kernel<8>, grid_for(n, 256 / 8, c.sms * 8), 256, 0, P, prow, Q, qrow, n, nch, ld, active, out);
     }
 }
 
@@ -200,13 +200,14 @@ void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, c
     const int nch = ld / 2;
     const int NCH = (nch + 31) / 32;
     PCR_REQUIRE(NCH <= 4, "rank too large for rowsum kernel (k <= 256)");
+    const char *rs_name = widx ? "rowsum_items" : (active ? "rowsum_users_active" : "rowsum_users");
     if (n_units > 0) {
         const unsigned grid = grid_for(n_units, 8, c.sms * 8);
         switch (NCH) {
-            case 1: LAUNCH(c, "rowsum", bytes, rowsum_kernel<1>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
-            case 2: LAUNCH(c, "rowsum", bytes, rowsum_kernel<2>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
-            case 3: LAUNCH(c, "rowsum", bytes, rowsum_kernel<3>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
-            default: LAUNCH(c, "rowsum", bytes, rowsum_kernel<4>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+            case 1: LAUNCH(c, rs_name, bytes, rowsum_kernel<1>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+            case 2: LAUNCH(c, rs_name, bytes, rowsum_kernel<2>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+            case 3: LAUNCH(c, rs_name, bytes, rowsum_kernel<3>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+            default: LAUNCH(c, rs_name, bytes, rowsum_kernel<4>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
         }
     }
     if (n_seg > 0)
