@@ -241,3 +241,42 @@ def test_large_scale_properties():
     e1, _, _ = make_engine(ds, k, lam, solver=1, U=Ug, V=Vg)
     assert abs(e1.initial_objective() - prev) / prev < 1e-10
     e.close(); e1.close()
+
+
+@pytest.mark.parametrize("solver", [2, 1])
+@pytest.mark.parametrize("name", ["tiny", "ml1m600", "toy400"])
+def test_golden_fixture_from_the_reference(name, solver):
+    """CUDA path against outputs of the UNMODIFIED reference (tests/golden/*.npz): stage outputs at the initial
+    point, objective / error / NDCG per outer iteration, final factors.  toy400 has real-valued ratings (9 lround
+    levels for Primal-CR++, exact-double comparisons for Primal-CR and the evaluation)."""
+    import os
+    from primalcr_b200.data import Ratings
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_%s.npz" % name))
+    d1, d2, k, lam, iters = int(g["d1"]), int(g["d2"]), int(g["k"]), float(g["lam"]), int(g["iters"])
+    train = Ratings(d1, d2, g["row_ptr"], g["item"], g["rating"])
+    p = api.Parameter(solver_type=solver, k=k, lambda_=lam, maxiter=iters)
+    e = api.Engine(p)
+    e.set_train(train)                      # level table derived by the library itself here
+    has_test = len(g["t_item"]) > 0
+    if has_test:
+        e.set_test(Ratings(d1, d2, g["t_row_ptr"], g["t_item"], g["t_rating"]))
+    e.set_factors(g["U0"], g["V0"])
+    assert rel(e.scores(), g["m0"]) < 1e-13
+    o0 = e.initial_objective()
+    assert abs(o0 - float(g["obj%d" % solver])) <= 1e-12 * o0
+    assert rel(e.grad_V(), g["g%d" % solver]) < VEC_TOL
+    assert rel(e.hv_V(g["dir_a"]), g["Ha%d" % solver]) < VEC_TOL
+    tr = e.eval(0)
+    assert np.allclose(tr, g["eval_train0"], rtol=0, atol=1e-12)
+    want, evals = g["s%d_obj" % solver], g["s%d_evals" % solver]
+    for i in range(1, iters + 1):
+        o = e.outer_iteration()
+        assert abs(o - want[i]) <= OBJ_TOL * abs(want[i]), i
+        err, ndcg = e.eval(0)
+        assert abs(err - evals[i, 0]) < 1e-9 and abs(ndcg - evals[i, 1]) < NDCG_TOL
+        if has_test:
+            err, ndcg = e.eval(1)
+            assert abs(err - evals[i, 2]) < 1e-9 and abs(ndcg - evals[i, 3]) < NDCG_TOL
+    U, V = e.get_factors()
+    assert rel(U, g["s%d_U" % solver]) < 1e-7 and rel(V, g["s%d_V" % solver]) < 1e-7
+    e.close()

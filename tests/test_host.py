@@ -1,0 +1,111 @@
+"""CPU tests of the host-side logic: file formats, model layout, sharding, the C-ABI library's exports."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+from primalcr_b200 import api
+from primalcr_b200.data import (Dataset, Ratings, load_model, read_reference_dir, save_model, shard_bounds,
+                                synth_dataset, write_reference_dir)
+from tests.util import dataset
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    txt = open(os.path.join(ROOT, "include", "primalcr.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(primalcr_[a-z_A-Z0-9]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = api.lib()
+    names = header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(api.SYMBOLS) == names
+    assert b"sm_100a" in L.primalcr_version()
+
+
+def test_compute_entry_points_fail_loudly_without_gpu(have_gpu):
+    if have_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.PrimalCRError, match="no CPU fallback|CUDA"):
+        api.Engine(api.Parameter(k=4))
+
+
+def test_reference_init_matches_golden_stream():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_tiny.npz"))
+    U = api.reference_init(int(g["d1"]), int(g["k"]))
+    assert np.array_equal(U, g["U0"])          # same libstdc++ engine + distribution => same bits as the reference CLI
+    if ob.reference() is not None:
+        assert np.array_equal(api.reference_init(50, 3), ob.ref_initial(50, 3))
+
+
+def test_reference_dir_roundtrip(tmp_path):
+    ds = dataset("tiny")
+    write_reference_dir(str(tmp_path / "d"), ds)
+    back = read_reference_dir(str(tmp_path / "d"))
+    for a, b in ((ds.train, back.train), (ds.test, back.test)):
+        assert np.array_equal(a.row_ptr, b.row_ptr) and np.array_equal(a.item, b.item) and np.array_equal(a.rating, b.rating)
+    meta = open(tmp_path / "d" / "meta").read().split()
+    assert meta[:4] == [str(ds.d1), str(ds.d2), str(ds.train.nnz), "training.ratings"]
+
+
+def test_unsorted_training_file_is_sorted_like_the_reference(tmp_path):
+    ds = dataset("tiny")
+    d = tmp_path / "d"; write_reference_dir(str(d), Dataset(ds.train, Ratings.empty(ds.d1, ds.d2)))
+    lines = open(d / "training.ratings").read().splitlines()
+    rng = np.random.default_rng(0); rng.shuffle(lines)
+    open(d / "training.ratings", "w").write("\n".join(lines) + "\n")
+    back = read_reference_dir(str(d))
+    assert np.array_equal(back.train.item, ds.train.item) and np.array_equal(back.train.rating, ds.train.rating)
+
+
+def test_model_file_layout(tmp_path):
+    rng = np.random.default_rng(1)
+    U, V = rng.standard_normal((7, 3)), rng.standard_normal((5, 3))
+    p = str(tmp_path / "m.model")
+    save_model(p, U, V)
+    raw = open(p, "rb").read()
+    assert len(raw) == 32 + 8 * 3 * (7 + 5)                       # util.cpp:30-51
+    assert np.frombuffer(raw[:16], np.int64).tolist() == [7, 3]
+    U2, V2 = load_model(p)
+    assert np.array_equal(U, U2) and np.array_equal(V, V2)
+    exe = ob.ref_cli("omp-pmf-predict")
+    if exe:                                                        # the reference's own predictor reads our model
+        t = tmp_path / "t.ratings"; t.write_text("1 1 3\n7 5 2\n3 2 5\n")
+        subprocess.run([exe, str(t), p, str(tmp_path / "out")], check=True)
+        got = np.loadtxt(tmp_path / "out")
+        want = np.array([U[0] @ V[0], U[6] @ V[4], U[2] @ V[1]])
+        assert np.allclose(got, want, atol=1e-6)
+
+
+def test_shard_bounds_balance_and_cover():
+    ds = synth_dataset("ml1m")
+    rp = ds.train.row_ptr
+    for world in (1, 2, 4, 8):
+        b = shard_bounds(rp, world)
+        assert b[0] == 0 and b[-1] == ds.d1 and np.all(np.diff(b) >= 0) and len(b) == world + 1
+        nnz = np.diff(rp[b])
+        assert nnz.sum() == ds.train.nnz
+        assert nnz.max() <= ds.train.nnz / world + ds.train.lens().max()
+    parts = [ds.train.slice_users(int(b[r]), int(b[r + 1])) for r in range(8)]
+    assert sum(p.nnz for p in parts) == ds.train.nnz
+    assert np.array_equal(np.concatenate([p.item for p in parts]), ds.train.item)
+
+
+def test_synthetic_generator_is_deterministic_and_well_formed():
+    a, b = synth_dataset("tiny"), synth_dataset("tiny")
+    assert np.array_equal(a.train.item, b.train.item) and np.array_equal(a.train.rating, b.train.rating)
+    R = a.train
+    assert R.rating.min() >= 1 and R.rating.max() <= 5 and R.item.max() < R.d2
+    for u in range(R.d1):
+        it = R.item[R.row_ptr[u]:R.row_ptr[u + 1]]
+        assert np.all(np.diff(it) > 0)                              # ascending, no duplicates (util.h:240)
+    pl = synth_dataset("powerlaw", scale=0.0005)
+    assert pl.train.lens().max() <= 100_000
