@@ -280,3 +280,36 @@ def test_golden_fixture_from_the_reference(name, solver):
     U, V = e.get_factors()
     assert rel(U, g["s%d_U" % solver]) < 1e-7 and rel(V, g["s%d_V" % solver]) < 1e-7
     e.close()
+
+
+@pytest.mark.parametrize("solver", [2, 1])
+def test_dropin_cli_reference_main_with_our_solver(tmp_path, solver):
+    """The reference's UNMODIFIED pmf-train.cpp linked against our pcr()/pcrpp() (shim + libprimalcr_b200.so):
+    same command line, same data directory, same stdout lines (6 digits) and the same model file layout."""
+    import os
+    import subprocess
+    from primalcr_b200.data import Dataset, Ratings, load_model, write_reference_dir
+    exe = ob.ref_cli("gpu-omp-pmf-train")
+    if exe is None:
+        pytest.skip("oracle/_ref/gpu-omp-pmf-train was not built (needs /root/reference at build time)")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_tiny.npz"))
+    d1, d2, k, lam, iters = int(g["d1"]), int(g["d2"]), int(g["k"]), float(g["lam"]), int(g["iters"])
+    ds = Dataset(Ratings(d1, d2, g["row_ptr"], g["item"], g["rating"]), Ratings(d1, d2, g["t_row_ptr"], g["t_item"], g["t_rating"]))
+    write_reference_dir(str(tmp_path / "data"), ds)
+    out = subprocess.run([exe, "-s", str(solver), "-k", str(k), "-l", str(lam), "-t", str(iters), "-p", "1", "-n", "1",
+                          str(tmp_path / "data"), str(tmp_path / "model")], cwd=tmp_path, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    ours = [l for l in out.stdout.splitlines() if l.startswith(("Iter", "(Training)", "(Testing)"))]
+    ref = [l for l in str(g["s%d_stdout" % solver]).splitlines() if l.startswith(("Iter", "(Training)", "(Testing)"))]
+    assert len(ours) == len(ref) == 3 * (iters + 1)
+    for a, b in zip(ours, ref):
+        ta, tb = a.split(), b.split()
+        assert ta[0] == tb[0]
+        if ta[0] == "Iter":
+            assert ta[1] == tb[1] and abs(float(ta[-1]) - float(tb[-1])) <= 2e-5 * abs(float(tb[-1]))
+        else:
+            assert abs(float(ta[4]) - float(tb[4])) < 2e-5 and abs(float(ta[-1]) - float(tb[-1])) < NDCG_TOL
+    U, V = load_model(str(tmp_path / "model"))
+    assert U.shape == (d1, k) and V.shape == (d2, k)
+    assert rel(U, g["s%d_U" % solver]) < 1e-7 and rel(V, g["s%d_V" % solver]) < 1e-7
+    assert os.path.exists(tmp_path / ("U.txt" if solver == 2 else "U%d.txt" % int(lam)))
