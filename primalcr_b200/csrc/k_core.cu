@@ -32,6 +32,18 @@ static inline unsigned grid_for(i64 work_items, int per_block, int max_blocks) {
     return (unsigned)b;
 }
 
+// grid of a persistent (grid-stride) kernel: exactly what fits at once, so there is a single full wave
+template <typename K>
+static unsigned resident_grid(K kernel, int block, size_t smem, int sms, i64 max_useful) {
+    int per_sm = 0;
+    PCR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+    if (per_sm < 1) per_sm = 1;
+    i64 g = (i64)per_sm * sms;
+    if (g > max_useful) g = max_useful;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
 // ------------------------------------------------------------------ block primitives
 
 // a[0..n) -> exclusive prefix sums in place, a[n] = total.  Fixed summation tree => deterministic.
@@ -122,9 +134,9 @@ void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const
     if (n <= 0) return;
     const int nch = ld / 2;
     if (nch <= 4) {
-        LAUNCH(c, active ? "dots_active" : "dots", bytes, dots_kernel<4>, grid_for(n, 256 / 4, c.sms * 8), 256, 0, P, prow, Q, qrow, n, nch, ld, active, out);
+        LAUNCH(c, active ? "dots_active" : "dots", bytes, dots_kernel<4>, resident_grid(dots_kernel<4>, 256, 0, c.sms, (n + 63) / 64), 256, 0, P, prow, Q, qrow, n, nch, ld, active, out);
     } else {
-        LAUNCH(c, active ? "dots_active" : "dots", bytes, dots_kernel<8>, grid_for(n, 256 / 8, c.sms * 8), 256, 0, P, prow, Q, qrow, n, nch, ld, active, out);
+        LAUNCH(c, active ? "dots_active" : "dots", bytes, dots_kernel<8>, resident_grid(dots_kernel<8>, 256, 0, c.sms, (n + 31) / 32), 256, 0, P, prow, Q, qrow, n, nch, ld, active, out);
     }
 }
 
@@ -202,7 +214,13 @@ void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, c
     PCR_REQUIRE(NCH <= 4, "rank too large for rowsum kernel (k <= 256)");
     const char *rs_name = widx ? "rowsum_items" : (active ? "rowsum_users_active" : "rowsum_users");
     if (n_units > 0) {
-        const unsigned grid = grid_for(n_units, 8, c.sms * 8);
+        unsigned grid = 1;
+        switch (NCH) {
+            case 1: grid = resident_grid(rowsum_kernel<1>, 256, 0, c.sms, (n_units + 7) / 8); break;
+            case 2: grid = resident_grid(rowsum_kernel<2>, 256, 0, c.sms, (n_units + 7) / 8); break;
+            case 3: grid = resident_grid(rowsum_kernel<3>, 256, 0, c.sms, (n_units + 7) / 8); break;
+            default: grid = resident_grid(rowsum_kernel<4>, 256, 0, c.sms, (n_units + 7) / 8); break;
+        }
         switch (NCH) {
             case 1: LAUNCH(c, rs_name, bytes, rowsum_kernel<1>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
             case 2: LAUNCH(c, rs_name, bytes, rowsum_kernel<2>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
