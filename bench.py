@@ -227,20 +227,20 @@ def main_ours(args):
     h_rp, h_it, h_ra = pin(shard.row_ptr.astype(np.int64)), pin(shard.item.astype(np.int32)), pin(shard.rating)
     h_U, h_V = pin(U_host), pin(V_host)
 
-    uid = None
-    if world > 1:
+    def fresh_uid():
+        """A ncclUniqueId serves ONE communicator: rank 0 makes a new one per engine, torch.distributed carries it."""
         buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             buf.copy_(torch.frombuffer(bytearray(api.Engine.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(buf, 0)
-        uid = bytes(buf.cpu().numpy().tobytes())
+        return bytes(buf.cpu().numpy().tobytes())
 
     def new_engine(maxiter):
         p = api.Parameter(solver_type=api.PCRPP, k=k, lambda_=lam, maxiter=maxiter, do_predict=0, device=local)
         e = api.Engine(p)
         e.set_levels(levels)
         if world > 1:
-            e.comm_init(rank, world, uid)
+            e.comm_init(rank, world, fresh_uid())
         return e
 
     def barrier():

@@ -95,6 +95,8 @@ struct DevPool {
     ~DevPool() { release(); }
 };
 
+struct TileList { int32_t *first = nullptr, *nusers = nullptr; i64 n = 0, nnz = 0; };
+
 // ------------------------------------------------------------------ a ratings set on the device (CSR by user)
 struct DevCsr {
     i64 d1 = 0, nnz = 0;
@@ -111,6 +113,8 @@ struct DevCsr {
     i64 heavy_total = 0;         // sum over heavy users of (len + 1)
     i64 *heavy_begin = nullptr, *heavy_end = nullptr;  // [n_cls[2]] absolute segment bounds (CUB segmented sort)
     i64 max_len = 0;
+    // tiles of consecutive users: [0] small (<= TILE_CAP ratings in total), [1] large (users with TILE_CAP < len <= TILE_CAP_L)
+    TileList tiles[2];
     // pair-tile work items (Primal-CR pair kernels and pairwise-error evaluation)
     int32_t *pt_user = nullptr; int32_t *pt_j0 = nullptr; i64 n_pt = 0;
     i64 *pt_ptr = nullptr;       // [d1+1] first work item of each user
@@ -127,6 +131,9 @@ struct SortedMeta {          // per rating, in (user, ascending score) order
     int32_t *cnt_lo = nullptr, *cnt_hi = nullptr;
 };
 
+static const int TILE_CAP = 1024;        // ratings per tile of consecutive users (k_tiles.cu)
+static const int TILE_MAX_USERS = 128;   // users per tile
+static const int TILE_CAP_L = 4096;      // large tiles: 1024 threads
 static const int S_CAP = 1024;   // block class  (256 threads, shared memory)
 static const int L_CAP = 4096;   // large class  (1024 threads, shared memory)
 static const int ROWSUM_CHUNK = 256;

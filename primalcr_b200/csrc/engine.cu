@@ -61,10 +61,11 @@ struct Engine {
     std::vector<i64> levels;
     bool levels_user_set = false;
     DevCsr X, XT;
-    bool has_train = false, has_test = false, has_factors = false;
+    bool has_train = false, has_test = false, has_factors = false, use_tiles = true;
     // CSC of the training set (by item)
     i64 *col_ptr = nullptr; int32_t *csc_user = nullptr, *csc2csr = nullptr;
-    int32_t *cu_seg = nullptr; i64 *cu_start = nullptr; i64 n_cunits = 0; i64 *col_unit_ptr = nullptr;
+    int32_t *cu_seg = nullptr; i64 *cu_start = nullptr, *cu_end = nullptr; i64 n_cunits = 0; i64 *col_unit_ptr = nullptr;
+    int32_t *col_unit_idx = nullptr; int n_user_blocks = 1;
     // factors (padded leading dimension ld)
     double *U = nullptr, *V = nullptr;
     // per-rating work buffers
@@ -227,12 +228,29 @@ struct Engine {
         std::vector<int32_t> cls[3];
         std::vector<i64> hoff((size_t)d1, -1), hb, he;
         i64 htot = 0;
+        use_tiles = (T <= 8) && (getenv("PRIMALCR_NO_TILES") == nullptr);
+        // tiles: runs of consecutive users; geometry 0 takes users with len <= TILE_CAP, geometry 1 users with
+        // TILE_CAP < len <= TILE_CAP_L; anything longer goes to the per-user heavy class
+        struct Builder { std::vector<int32_t> first, num; i64 cur_first = -1, cur_nnz = 0, cur_users = 0, nnz = 0; i64 cap;
+            void close() { if (cur_first >= 0 && cur_nnz > 0) { first.push_back((int32_t)cur_first); num.push_back((int32_t)cur_users); nnz += cur_nnz; }
+                           cur_first = -1; cur_nnz = 0; cur_users = 0; }
+            void add(i64 u, i64 len) { if (cur_first >= 0 && (cur_nnz + len > cap || cur_users + 1 > TILE_MAX_USERS)) close();
+                                       if (cur_first < 0) cur_first = u; cur_nnz += len; cur_users += 1; } };
+        Builder tb[2]; tb[0].cap = TILE_CAP; tb[1].cap = TILE_CAP_L;
         for (i64 u = 0; u < d1; ++u) {
             const i64 len = X.h_row_ptr[u + 1] - X.h_row_ptr[u];
+            if (use_tiles && len <= TILE_CAP) { tb[1].close(); tb[0].add(u, len); continue; }
+            if (use_tiles && T <= 5 && len <= TILE_CAP_L) { tb[0].close(); tb[1].add(u, len); continue; }   // T>5: smem
+            tb[0].close(); tb[1].close();
             if (len == 0) continue;
             if (len <= S_CAP) cls[0].push_back((int32_t)u);
             else if (len <= L_CAP) cls[1].push_back((int32_t)u);
             else { cls[2].push_back((int32_t)u); hoff[u] = htot; htot += len + 1; hb.push_back(X.h_row_ptr[u]); he.push_back(X.h_row_ptr[u + 1]); }
+        }
+        for (int gq = 0; gq < 2; ++gq) {
+            tb[gq].close();
+            X.tiles[gq].n = (i64)tb[gq].first.size(); X.tiles[gq].nnz = tb[gq].nnz;
+            X.tiles[gq].first = upload_vec(tb[gq].first); X.tiles[gq].nusers = upload_vec(tb[gq].num);
         }
         for (int q = 0; q < 3; ++q) { X.n_cls[q] = (int)cls[q].size(); X.cls_users[q] = upload_vec(cls[q]); }
         X.heavy_off = upload_vec(hoff); X.heavy_total = htot;
@@ -254,10 +272,45 @@ struct Engine {
         PCR_CUDA(cudaMemcpyAsync(h_col.data(), col_ptr, sizeof(i64) * ((size_t)d2 + 1), cudaMemcpyDeviceToHost, stream));
         sync();
         PCR_REQUIRE(h_col[d2] == nnz, "item id out of range [0, d2)");
-        std::vector<int32_t> cseg; std::vector<i64> cstart, csup;
-        make_units(h_col, cseg, cstart, csup);
-        n_cunits = (i64)cseg.size();
-        cu_seg = upload_vec(cseg); cu_start = upload_vec(cstart); col_unit_ptr = upload_vec(csup);
+        // Work units of the item-major row sum, ordered USER-BLOCK-major: every unit only touches U rows of one block
+        // of <= ~40 MB, so while the persistent grid walks the unit list the gathered rows stay L2-resident
+        // (users ascend inside a column, so a column's entries of one block are contiguous).
+        {
+            const double u_bytes = (double)d1 * ld * 8.0;
+            const double blk_bytes = getenv("PRIMALCR_UBLOCK_MB") ? atof(getenv("PRIMALCR_UBLOCK_MB")) * 1e6 : 40e6;
+            int nb = (int)std::ceil(u_bytes / blk_bytes);
+            if (nb < 1) nb = 1;
+            if (nb > 64) nb = 64;
+            const i64 bu = (d1 + nb - 1) / nb > 0 ? (d1 + nb - 1) / nb : 1;
+            n_user_blocks = nb;
+            std::vector<i64> bpos((size_t)d2 * (nb + 1));
+            i64 *bpos_d = nullptr;
+            PCR_CUDA(cudaMalloc(&bpos_d, sizeof(i64) * bpos.size()));
+            k_csc_block_bounds(ctx, col_ptr, csc_user, d2, nb, bu, bpos_d);
+            PCR_CUDA(cudaMemcpyAsync(bpos.data(), bpos_d, sizeof(i64) * bpos.size(), cudaMemcpyDeviceToHost, stream));
+            sync();
+            cudaFree(bpos_d);
+            std::vector<int32_t> cseg, cidx; std::vector<i64> cstart, cend, csup((size_t)d2 + 1, 0);
+            for (int blk = 0; blk < nb; ++blk)
+                for (i64 pcol = 0; pcol < d2; ++pcol) {
+                    const i64 lo = bpos[(size_t)pcol * (nb + 1) + blk], hi = blk + 1 == nb ? h_col[pcol + 1] : bpos[(size_t)pcol * (nb + 1) + blk + 1];
+                    // popular items get longer units so that no item has more than ~48 + nb partial sums to add up
+                    const i64 collen = h_col[pcol + 1] - h_col[pcol];
+                    const i64 chunk = std::max<i64>(ROWSUM_CHUNK, (collen + 47) / 48);
+                    for (i64 bb = lo; bb < hi; bb += chunk) {
+                        cseg.push_back((int32_t)pcol); cstart.push_back(bb); cend.push_back(std::min(bb + chunk, hi));
+                        csup[pcol + 1] += 1;
+                    }
+                }
+            n_cunits = (i64)cseg.size();
+            for (i64 pcol = 0; pcol < d2; ++pcol) csup[pcol + 1] += csup[pcol];
+            cidx.resize(cseg.size());
+            std::vector<i64> fill(csup.begin(), csup.end() - 1);
+            for (size_t uu = 0; uu < cseg.size(); ++uu) cidx[fill[cseg[uu]]++] = (int32_t)uu;
+            cu_seg = upload_vec(cseg); cu_start = upload_vec(cstart); cu_end = upload_vec(cend);
+            col_unit_ptr = upload_vec(csup); col_unit_idx = upload_vec(cidx);
+            sync();
+        }
         // ---- work buffers
         m = pool.alloc<double>((size_t)nnz); b = pool.alloc<double>((size_t)nnz); cbuf = pool.alloc<double>((size_t)nnz);
         meta.s = pool.alloc<double>((size_t)nnz); meta.pos = pool.alloc<int32_t>((size_t)nnz);
@@ -339,7 +392,7 @@ struct Engine {
         PCR_REQUIRE(has_train, "load the training set first");
         put_matrix(Uh, d1, U); put_matrix(Vh, d2, V);
         sync();
-        has_factors = true; scores_valid = false; meta_valid = false;
+        has_factors = true; scores_valid = false; meta_valid = false; loss_matches_m = false; last_m_is_stale = false;
     }
     void get_factors(double *Uh, double *Vh) {
         bind();
@@ -371,10 +424,17 @@ struct Engine {
 
     // scores of all training ratings under (Um, Vm): comp_m_new pcrpp.cpp:17-35
     void scores(const double *Um, const double *Vm, double *out, const uint8_t *active) {
-        k_dots(ctx, Um, X.user, Vm, X.item, X.nnz, ld, active, out, active ? 0.0 : pass_bytes(X.nnz, d1));
+        train_dots(Um, Vm, out, active);
+    }
+    // out[e] = P[user(e)] . Q[item(e)] over the training set
+    void train_dots(const double *P, const double *Q, double *out, const uint8_t *active) {
+        const double bytes = active ? 0.0 : pass_bytes(X.nnz, d1);
+        if (!k_dots_units(ctx, X.un_seg, X.un_start, X.n_units, P, Q, X.item, ld, active, out, bytes))
+            k_dots(ctx, P, X.user, Q, X.item, X.nnz, ld, active, out, bytes);
     }
     // get_sorted_mm + window pointers for every (active) user
     void prepare(const double *sc, const uint8_t *active) {
+        for (int gq = 0; gq < 2; ++gq) k_tile_prepare(ctx, X, gq, active, sc, meta, T);
         k_sort_users(ctx, 0, X.cls_users[0], X.n_cls[0], active, X.row_ptr, sc, X.level, meta);
         k_sort_users(ctx, 1, X.cls_users[1], X.n_cls[1], active, X.row_ptr, sc, X.level, meta);
         if (X.n_cls[2] > 0) {
@@ -386,10 +446,12 @@ struct Engine {
         meta_valid = true;
     }
     void sweep_coeff(int mode, const uint8_t *active, const double *bsrc) {
+        for (int gq = 0; gq < 2; ++gq) k_tile_sweep(ctx, mode, X, gq, active, meta, bsrc, cbuf, nullptr, T);
         for (int q = 0; q < 3; ++q)
             k_sweep_coeff(ctx, q, mode, X.cls_users[q], X.n_cls[q], active, X.row_ptr, meta, bsrc, cbuf, T, X.heavy_off, h_v, h_p1, h_acc);
     }
     void sweep_obj(const uint8_t *active) {
+        for (int gq = 0; gq < 2; ++gq) k_tile_sweep(ctx, 2, X, gq, active, meta, nullptr, nullptr, us.loss, T);
         for (int q = 0; q < 3; ++q)
             k_sweep_obj(ctx, q, X.cls_users[q], X.n_cls[q], active, X.row_ptr, meta, us.loss, T, X.heavy_off, h_p1, h_p2, h_acc);
     }
@@ -417,10 +479,10 @@ struct Engine {
     void rowsum_items(const double *x, double *out) {
         const double bytes = pass_bytes(X.nnz, d2);
         if (world <= 1) {
-            k_rowsum(ctx, cu_seg, cu_start, n_cunits, col_unit_ptr, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
+            k_rowsum(ctx, cu_seg, cu_start, cu_end, n_cunits, col_unit_ptr, col_unit_idx, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
                      cfg.lambda, x, out, 0, bytes);
         } else {
-            k_rowsum(ctx, cu_seg, cu_start, n_cunits, col_unit_ptr, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
+            k_rowsum(ctx, cu_seg, cu_start, cu_end, n_cunits, col_unit_ptr, col_unit_idx, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
                      0.0, nullptr, out, 0, bytes);
             allreduce(out, (size_t)d2 * ld);
             k_axpby(ctx, out, 1.0, out, cfg.lambda, x, d2 * ld);
@@ -428,7 +490,7 @@ struct Engine {
     }
     // out[i] = lambda*x[i] + sum over user i of cbuf[e] * V[item(e)]   (U-side gradient / Hessian-vector product)
     void rowsum_users(const double *x, double *out, const uint8_t *active, int zero_if_empty) {
-        k_rowsum(ctx, X.un_seg, X.un_start, X.n_units, X.seg_unit_ptr, d1, X.item, nullptr, cbuf, V, ld, active, partial,
+        k_rowsum(ctx, X.un_seg, X.un_start, nullptr, X.n_units, X.seg_unit_ptr, nullptr, d1, X.item, nullptr, cbuf, V, ld, active, partial,
                  cfg.lambda, x, out, zero_if_empty, active ? 0.0 : pass_bytes(X.nnz, d1));
     }
 
@@ -436,7 +498,7 @@ struct Engine {
         PCR_REQUIRE(has_train && has_factors, "engine needs a training set and factors");
         bind();
     }
-    void ensure_scores() { if (!scores_valid) { scores(U, V, m, nullptr); scores_valid = true; meta_valid = false; } }
+    void ensure_scores() { if (!scores_valid) { scores(U, V, m, nullptr); scores_valid = true; meta_valid = false; loss_matches_m = false; } }
     void ensure_meta() { ensure_scores(); if (cfg.solver == 2 && !meta_valid) prepare(m, nullptr); }
 
     // ------------------------------------------------------------------ stage entry points
@@ -452,7 +514,7 @@ struct Engine {
     }
     void hv_V(const double *a_dev, double *out_dev) {   // compute_Ha_new / compute_Ha
         require_ready(); ensure_meta();
-        k_dots(ctx, U, X.user, a_dev, X.item, X.nnz, ld, nullptr, b, pass_bytes(X.nnz, d1));
+        train_dots(U, a_dev, b, nullptr);
         coeffs(1, nullptr);
         rowsum_items(a_dev, out_dev);
     }
@@ -477,7 +539,7 @@ struct Engine {
         const double err = std::sqrt(h_slots[0]) * 0.01;
         int its = 0;
         for (int it = 1; it <= 10; ++it) {
-            k_dots(ctx, U, X.user, p, X.item, X.nnz, ld, nullptr, b, pass_bytes(X.nnz, d1));
+            train_dots(U, p, b, nullptr);
             coeffs(1, nullptr);
             rowsum_items(p, Hp);
             ++its;
@@ -510,12 +572,14 @@ struct Engine {
         }
         // m (and the sorted state) are those of the LAST trial, accepted or not -- as in the reference (:443)
         scores_valid = accepted != 0;   // if rejected, m belongs to a V that was thrown away
+        loss_matches_m = true;
         counters.v_cg_iters = its; counters.v_ls_trials = trials; counters.v_ls_accepted = accepted;
         v_accepted = accepted;
         last_m_is_stale = !accepted;
         return now_obj;
     }
     bool last_m_is_stale = false;
+    bool loss_matches_m = false;   // us.loss == per-user losses of the scores in m (set by update_V's last trial)
 
     // ------------------------------------------------------------------ update_U(_new), batched over users
     double update_U() {
@@ -527,18 +591,19 @@ struct Engine {
         // prev_obj: Primal-CR++ takes it from the same sorted state (objective_u_new :785); Primal-CR recomputes
         // the scores with the current (u_i, V) (compute_mm pcr.cpp:549), which differs only if V's search failed
         if (cfg.solver == 1 && last_m_is_stale) {
-            k_dots(ctx, U, X.user, V, X.item, X.nnz, ld, nullptr, b, pass_bytes(X.nnz, d1));
+            train_dots(U, V, b, nullptr);
             user_losses(b, nullptr);
-        } else {
-            user_losses(m, nullptr);
+        } else if (!loss_matches_m) {
+            user_losses(m, nullptr);      // else: us.loss still holds the losses of these very scores (last V trial)
         }
+        loss_matches_m = false;
         rowsum_users(U, us.g, nullptr, 1);
         zero_counters();
         k_u_init(ctx, us, U, X.row_ptr, cfg.solver == 1 ? has_pairs : nullptr, d1, ld, cfg.lambda);
         int n_active = read_counter(0);
         // ---- solve_delta_u(_new): <= 10 CG iterations, each user leaves when its residual test fires
         for (int it = 1; it <= 10 && n_active > 0; ++it) {
-            k_dots(ctx, us.p, X.user, V, X.item, X.nnz, ld, us.cg_active, b, 0.0);
+            train_dots(us.p, V, b, us.cg_active);
             coeffs(1, us.cg_active);
             rowsum_users(us.p, us.Hp, us.cg_active, 0);
             zero_counters();
@@ -552,7 +617,7 @@ struct Engine {
             k_u_ls_trial(ctx, us, U, d1, ld, cfg.stepsize, trial == 0);
             if (trial == 0) { n_ls = read_counter(1); if (n_ls == 0) break; }
             double *dst = cfg.solver == 2 ? m : b;
-            k_dots(ctx, us.Unew, X.user, V, X.item, X.nnz, ld, us.ls_active, dst, 0.0);
+            train_dots(us.Unew, V, dst, us.ls_active);
             if (cfg.solver == 2) prepare(dst, us.ls_active);
             user_losses(dst, us.ls_active);
             zero_counters();
@@ -586,7 +651,7 @@ struct Engine {
     }
     void hv_U_stage(const double *S_dev, double *out_dev) {
         require_ready(); ensure_meta();
-        k_dots(ctx, S_dev, X.user, V, X.item, X.nnz, ld, nullptr, b, pass_bytes(X.nnz, d1));
+        train_dots(S_dev, V, b, nullptr);
         coeffs(1, nullptr);
         rowsum_users(S_dev, out_dev, nullptr, 0);
     }
@@ -820,7 +885,7 @@ int primalcr_scores(primalcr_engine *e, double *m_out) {
     CHECK_E(e) API_BEGIN
     Engine *E = e->impl;
     E->require_ready();
-    E->scores(E->U, E->V, E->m, nullptr); E->scores_valid = true; E->meta_valid = false; E->last_m_is_stale = false;
+    E->scores(E->U, E->V, E->m, nullptr); E->scores_valid = true; E->meta_valid = false; E->last_m_is_stale = false; E->loss_matches_m = false;
     if (m_out && E->X.nnz) PCR_CUDA(cudaMemcpyAsync(m_out, E->m, sizeof(double) * (size_t)E->X.nnz, cudaMemcpyDeviceToHost, E->stream));
     E->sync();
     API_END
@@ -833,7 +898,7 @@ int primalcr_set_scores(primalcr_engine *e, const double *m) {
     PCR_REQUIRE(m != nullptr || E->X.nnz == 0, "null scores");
     if (E->X.nnz) PCR_CUDA(cudaMemcpyAsync(E->m, m, sizeof(double) * (size_t)E->X.nnz, cudaMemcpyHostToDevice, E->stream));
     E->sync();
-    E->scores_valid = true; E->meta_valid = false; E->last_m_is_stale = false;
+    E->scores_valid = true; E->meta_valid = false; E->last_m_is_stale = false; E->loss_matches_m = false;
     API_END
 }
 

@@ -140,10 +140,86 @@ void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const
     }
 }
 
+// user-major variant for the training set: one warp per (user, <=ROWSUM_CHUNK ratings) unit; the user's row P[seg]
+// stays in registers, the 32 item indices of a batch are fetched with one coalesced load, and the NC 16-byte loads of
+// a rating's Q row are issued back to back before the first FMA (NC is a template parameter => fully unrolled).
+template <int G, int NC>
+__global__ void __launch_bounds__(256) dots_units_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
+                                                         i64 n_units, const double *__restrict__ P,
+                                                         const double *__restrict__ Q, const int32_t *__restrict__ qrow,
+                                                         int nch, int ld, const uint8_t *__restrict__ active,
+                                                         double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int lg = lane % G, grp = lane / G;
+    constexpr int PW = 32 / G;
+    const i64 warp_global = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * 256) >> 5;
+    for (i64 u = warp_global; u < n_units; u += nwarps) {
+        const int seg = un_seg[u];
+        if (active && !active[seg]) continue;           // warp-uniform
+        const i64 b = un_start[u], e = un_start[u + 1];
+        double2 pr[NC];
+        const double2 *p2 = reinterpret_cast<const double2 *>(P + (size_t)seg * ld);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) { const int c = lg + G * i; pr[i] = c < nch ? __ldg(p2 + c) : make_double2(0.0, 0.0); }
+        for (i64 base = b; base < e; base += 32) {
+            const i64 me = base + lane;
+            const int qi = me < e ? qrow[me] : 0;
+            const int cnt = (e - base) < 32 ? (int)(e - base) : 32;
+#pragma unroll 2
+            for (int t = 0; t < cnt; t += PW) {
+                const int j = t + grp;
+                const bool valid = j < cnt;
+                const int r = __shfl_sync(FULL, qi, j & 31);
+                const double2 *q2 = reinterpret_cast<const double2 *>(Q + (size_t)r * ld);
+                double2 qv[NC];
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    const int c = lg + G * i;
+                    qv[i] = (valid && c < nch) ? __ldg(q2 + c) : make_double2(0.0, 0.0);
+                }
+                double ax = 0.0, ay = 0.0;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) { ax = fma(pr[i].x, qv[i].x, ax); ay = fma(pr[i].y, qv[i].y, ay); }
+                double sres = ax + ay;
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) sres += __shfl_xor_sync(FULL, sres, o);
+                if (valid && lg == 0) out[base + j] = sres;
+            }
+        }
+    }
+}
+
+template <int G, int NC>
+static void launch_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, const double *P, const double *Q,
+                              const int32_t *qrow, int nch, int ld, const uint8_t *active, double *out, double bytes) {
+    const unsigned grid = resident_grid(dots_units_kernel<G, NC>, 256, 0, c.sms, (n_units + 7) / 8);
+    LAUNCH(c, active ? "dots_active" : "dots", bytes, (dots_units_kernel<G, NC>), grid, 256, 0, un_seg, un_start, n_units, P, Q, qrow,
+           nch, ld, active, out);
+}
+
+// returns false when no specialisation fits (caller falls back to k_dots)
+bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, const double *P, const double *Q,
+                  const int32_t *qrow, int ld, const uint8_t *active, double *out, double bytes) {
+    if (n_units <= 0) return true;
+    const int nch = ld / 2;
+#define DU(G, NC) launch_dots_units<G, NC>(c, un_seg, un_start, n_units, P, Q, qrow, nch, ld, active, out, bytes); return true;
+    if (nch <= 56) {
+        switch ((nch + 7) / 8) { case 1: DU(8, 1) case 2: DU(8, 2) case 3: DU(8, 3) case 4: DU(8, 4) case 5: DU(8, 5) case 6: DU(8, 6) default: DU(8, 7) }
+    } else if (nch <= 112) {
+        switch ((nch + 15) / 16) { case 4: DU(16, 4) case 5: DU(16, 5) case 6: DU(16, 6) default: DU(16, 7) }
+    } else if (nch <= 224) {
+        switch ((nch + 31) / 32) { case 4: DU(32, 4) case 5: DU(32, 5) case 6: DU(32, 6) default: DU(32, 7) }
+    }
+#undef DU
+    return false;
+}
+
 // ------------------------------------------------------------------ K4: segmented weighted row sums
 
 template <int NCH>
 __global__ void __launch_bounds__(256) rowsum_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
+                                                     const i64 *__restrict__ un_end,
                                                      i64 n_units, const int32_t *__restrict__ ridx,
                                                      const int32_t *__restrict__ widx, const double *__restrict__ w,
                                                      const double *__restrict__ M, int ld, int nch,
@@ -154,7 +230,7 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const int32_t *__restrict__
     for (i64 u = warp_global; u < n_units; u += nwarps) {
         const int seg = un_seg[u];
         if (active && !active[seg]) continue;           // warp-uniform
-        const i64 b = un_start[u], e = un_start[u + 1];
+        const i64 b = un_start[u], e = un_end ? un_end[u] : un_start[u + 1];
         double2 acc[NCH];
 #pragma unroll
         for (int q = 0; q < NCH; ++q) acc[q] = make_double2(0.0, 0.0);
@@ -186,7 +262,8 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const int32_t *__restrict__
 }
 
 // out[seg] = lambda*x[seg] + partial[first unit] + partial[second unit] + ...   (fixed order)
-__global__ void __launch_bounds__(256) rowsum_finalize_kernel(const i64 *__restrict__ seg_unit_ptr, i64 n_seg,
+__global__ void __launch_bounds__(256) rowsum_finalize_kernel(const i64 *__restrict__ seg_unit_ptr,
+                                                              const int32_t *__restrict__ seg_unit_idx, i64 n_seg,
                                                               const double *__restrict__ partial, int ld,
                                                               const uint8_t *__restrict__ active, double lambda,
                                                               const double *__restrict__ x, double *__restrict__ out,
@@ -199,14 +276,21 @@ __global__ void __launch_bounds__(256) rowsum_finalize_kernel(const i64 *__restr
         const i64 u0 = seg_unit_ptr[seg], u1 = seg_unit_ptr[seg + 1];
         for (int cidx = lane; cidx < ld; cidx += 32) {
             double v = (x != nullptr && !(zero_if_empty && u0 == u1)) ? lambda * x[(size_t)seg * ld + cidx] : 0.0;
-            for (i64 u = u0; u < u1; ++u) v += partial[(size_t)u * ld + cidx];
+            i64 u = u0;
+            for (; u + 4 <= u1; u += 4) {       // 4 independent loads in flight, summed in unit order
+                double t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[q] = partial[(size_t)(seg_unit_idx ? seg_unit_idx[u + q] : u + q) * ld + cidx];
+                v += t[0]; v += t[1]; v += t[2]; v += t[3];
+            }
+            for (; u < u1; ++u) v += partial[(size_t)(seg_unit_idx ? seg_unit_idx[u] : u) * ld + cidx];
             out[(size_t)seg * ld + cidx] = v;
         }
     }
 }
 
-void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, const i64 *seg_unit_ptr, i64 n_seg,
-              const int32_t *ridx, const int32_t *widx, const double *w, const double *M, int ld,
+void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_end, i64 n_units, const i64 *seg_unit_ptr,
+              const int32_t *seg_unit_idx, i64 n_seg, const int32_t *ridx, const int32_t *widx, const double *w, const double *M, int ld,
               const uint8_t *active, double *partial, double lambda, const double *x, double *out,
               int zero_if_empty, double bytes) {
     const int nch = ld / 2;
@@ -222,14 +306,14 @@ void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, c
             default: grid = resident_grid(rowsum_kernel<4>, 256, 0, c.sms, (n_units + 7) / 8); break;
         }
         switch (NCH) {
-            case 1: LAUNCH(c, rs_name, bytes, rowsum_kernel<1>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
-            case 2: LAUNCH(c, rs_name, bytes, rowsum_kernel<2>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
-            case 3: LAUNCH(c, rs_name, bytes, rowsum_kernel<3>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
-            default: LAUNCH(c, rs_name, bytes, rowsum_kernel<4>, grid, 256, 0, un_seg, un_start, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+            case 1: LAUNCH(c, rs_name, bytes, rowsum_kernel<1>, grid, 256, 0, un_seg, un_start, un_end, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+            case 2: LAUNCH(c, rs_name, bytes, rowsum_kernel<2>, grid, 256, 0, un_seg, un_start, un_end, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+            case 3: LAUNCH(c, rs_name, bytes, rowsum_kernel<3>, grid, 256, 0, un_seg, un_start, un_end, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+            default: LAUNCH(c, rs_name, bytes, rowsum_kernel<4>, grid, 256, 0, un_seg, un_start, un_end, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
         }
     }
     if (n_seg > 0)
-        LAUNCH(c, "rowsum_finalize", 0.0, rowsum_finalize_kernel, grid_for(n_seg, 8, c.sms * 8), 256, 0, seg_unit_ptr, n_seg,
+        LAUNCH(c, "rowsum_finalize", 0.0, rowsum_finalize_kernel, grid_for(n_seg, 8, c.sms * 8), 256, 0, seg_unit_ptr, seg_unit_idx, n_seg,
                partial, ld, active, lambda, x, out, zero_if_empty);
 }
 

@@ -103,6 +103,22 @@ void k_build_csc(Ctx &c, DevPool &pool, const int32_t *item, const int32_t *user
     (void)pool;
 }
 
+__global__ void csc_block_bounds_kernel(const i64 *__restrict__ col_ptr, const int32_t *__restrict__ csc_user, i64 d2, int nb,
+                                        i64 block_users, i64 *__restrict__ bpos) {
+    const i64 total = d2 * (nb + 1);
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        const i64 p = t / (nb + 1); const int j = (int)(t - p * (nb + 1));
+        i64 a = col_ptr[p], b = col_ptr[p + 1];
+        const i64 key = (i64)j * block_users;
+        while (a < b) { const i64 mid = (a + b) >> 1; if ((i64)csc_user[mid] < key) a = mid + 1; else b = mid; }
+        bpos[t] = a;
+    }
+}
+void k_csc_block_bounds(Ctx &c, const i64 *col_ptr, const int32_t *csc_user, i64 d2, int nb, i64 block_users, i64 *bpos) {
+    if (d2 <= 0) return;
+    LAUNCH(c, "csc_block_bounds", 0.0, csc_block_bounds_kernel, grid_for(d2 * (nb + 1), 256, c.sms * 16), 256, 0, col_ptr, csc_user, d2, nb, block_users, bpos);
+}
+
 void k_heavy_sort(Ctx &c, DevPool &pool, void **temp, size_t *temp_bytes, const double *m, const int32_t *iota,
                   double *s_sorted, int32_t *pos_sorted, i64 nnz, int n_heavy, const i64 *begin, const i64 *end) {
     if (n_heavy <= 0) return;

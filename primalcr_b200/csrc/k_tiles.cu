@@ -1,0 +1,384 @@
+// k_tiles.cu -- "tile of users" kernels for the N-sized stages of Primal-CR++ (sort, windows, level sweeps).
+//
+// A tile is a run of consecutive users whose ratings (<= TILE_CAP in total) are handled by ONE 256-thread CTA as a
+// single array with segment boundaries, so thread utilisation does not depend on how short the users are (the
+// per-user kernels of k_core.cu keep serving users with more than TILE_CAP ratings).
+//
+//   tile_prepare  K2+K3  get_sorted_mm pcrpp.cpp:52-83 as one bitonic sort over (user, score, index) keys, then the
+//                        window pointers and integer level counters of the sweep pcrpp.cpp:214-229
+//   tile_sweep    K3     c_j of obtain_g_new :230-238 / compute_Ha_new :310-318 / obtain_g_u_new :527-535 /
+//                        obtain_Hs_new :613-621 and the objective :392-407 / :556-571
+//
+// Per-level exclusive prefix sums S_t(x) = sum_{q<x, l_q=t} v_q of one user are produced by a SEGMENTED blocked scan
+// (each thread owns TILE_E consecutive elements; a segment starts at a user's first element) and stored in shared
+// memory at slot (x + user_start + user_index): every user gets one extra slot for its totals S_t(n).
+#include "kernels.h"
+#include <math_constants.h>
+
+namespace pcr {
+
+#define FULL 0xffffffffu
+#define LAUNCH(ctx, name, bytes, kernel, grid, block, smem, ...)                         \
+    do {                                                                                 \
+        (ctx).prof->begin(name, (ctx).stream, (double)(bytes));                          \
+        kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);                  \
+        (ctx).prof->end((ctx).stream);                                                   \
+        PCR_CUDA(cudaGetLastError());                                                    \
+    } while (0)
+
+static const int TE = 4;                       // elements per thread (blocked); a tile holds TH * TE ratings
+// two geometries: small tiles (256 threads, 1024 ratings) and large tiles (1024 threads, 4096 ratings)
+
+template <int CAP>
+struct TileShared {
+    int ustart[TILE_MAX_USERS + 1];            // tile-local start of every user; ustart[n_users] = ne
+    uint8_t uact[TILE_MAX_USERS];              // user participates (active mask)
+    uint8_t ul[CAP];                           // user index (inside the tile) of every element, position order
+};
+
+// ---------------------------------------------------------------- segmented blocked scan of per-level streams
+// val(i) / lev(i): stream value and level of element i (i in sorted-position order, 0 <= i < ne).
+// Writes S[t * SLOTS + slot] for t < T, slot = i + ul[i] (exclusive prefix) and the per-user totals.
+template <typename VT, int TT, int TH, typename ValF, typename LevF>
+__device__ __forceinline__ void tile_level_scan(const TileShared<TH * TE> &ts, int ne, int T, VT *S, VT *wagg /* [TH/32*TT] */,
+                                                int *wflag /* [TH/32] */, ValF val, LevF lev) {
+    constexpr int SLOTS = TH * TE + TILE_MAX_USERS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lo = tid * TE;
+    VT agg[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) agg[t] = (VT)0;
+    int flag = 0;
+#pragma unroll
+    for (int q = 0; q < TE; ++q) {
+        const int i = lo + q;
+        if (i < ne) {
+            const int u = ts.ul[i];
+            if (i == ts.ustart[u]) {
+#pragma unroll
+                for (int t = 0; t < TT; ++t) agg[t] = (VT)0;
+                flag = 1;
+            }
+            const int l = lev(i);
+            const VT v = val(i);
+#pragma unroll
+            for (int t = 0; t < TT; ++t) agg[t] += (t == l) ? v : (VT)0;
+        }
+    }
+    // inclusive segmented warp scan of (agg, flag)
+    VT inc[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) inc[t] = agg[t];
+    int finc = flag;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int of = __shfl_up_sync(FULL, finc, o);
+#pragma unroll
+        for (int t = 0; t < TT; ++t) {
+            const VT ov = __shfl_up_sync(FULL, inc[t], o);
+            if (lane >= o && !finc) inc[t] += ov;
+        }
+        if (lane >= o) finc |= of;
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int t = 0; t < TT; ++t) wagg[warp * TT + t] = inc[t];
+        wflag[warp] = finc;
+    }
+    // exclusive within the warp
+    VT exc[TT];
+    int fexc = __shfl_up_sync(FULL, finc, 1);
+#pragma unroll
+    for (int t = 0; t < TT; ++t) { exc[t] = __shfl_up_sync(FULL, inc[t], 1); if (lane == 0) exc[t] = (VT)0; }
+    if (lane == 0) fexc = 0;
+    __syncthreads();
+    // carry from the previous warps (sequential over <= 8 entries, same order in every thread => deterministic)
+    VT carry[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) carry[t] = (VT)0;
+    for (int w = 0; w < warp; ++w) {
+        const int wf = wflag[w];
+#pragma unroll
+        for (int t = 0; t < TT; ++t) carry[t] = wf ? wagg[w * TT + t] : carry[t] + wagg[w * TT + t];
+    }
+#pragma unroll
+    for (int t = 0; t < TT; ++t) carry[t] = fexc ? exc[t] : carry[t] + exc[t];
+    // replay the chunk, emitting exclusive prefixes and the per-user totals
+#pragma unroll
+    for (int q = 0; q < TE; ++q) {
+        const int i = lo + q;
+        if (i < ne) {
+            const int u = ts.ul[i];
+            if (i == ts.ustart[u]) {
+#pragma unroll
+                for (int t = 0; t < TT; ++t) carry[t] = (VT)0;
+            }
+            const int slot = i + u;
+#pragma unroll
+            for (int t = 0; t < TT; ++t) if (t < T) S[t * SLOTS + slot] = carry[t];
+            const int l = lev(i);
+            const VT v = val(i);
+#pragma unroll
+            for (int t = 0; t < TT; ++t) carry[t] += (t == l) ? v : (VT)0;
+            if (i + 1 == ts.ustart[u + 1]) {
+#pragma unroll
+                for (int t = 0; t < TT; ++t) if (t < T) S[t * SLOTS + slot + 1] = carry[t];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// common tile set-up: user starts, active flags, element -> user map.  Returns ne (0 if nothing to do).
+template <int TH>
+__device__ __forceinline__ int tile_setup(TileShared<TH * TE> &ts, int first_user, int n_users, const i64 *__restrict__ row_ptr,
+                                          const int32_t *__restrict__ user_of, const uint8_t *__restrict__ active,
+                                          i64 &e0) {
+    const int tid = threadIdx.x;
+    e0 = row_ptr[first_user];
+    int any = 0;
+    for (int u = tid; u <= n_users; u += TH) {
+        ts.ustart[u] = (int)(row_ptr[first_user + u] - e0);
+        if (u < n_users) {
+            const uint8_t a = active ? active[first_user + u] : (uint8_t)1;
+            ts.uact[u] = a;
+            if (a && row_ptr[first_user + u + 1] > row_ptr[first_user + u]) any = 1;
+        }
+    }
+    any = __syncthreads_or(any);
+    if (!any) return 0;
+    const int ne = ts.ustart[n_users];
+    for (int i = tid; i < ne; i += TH) ts.ul[i] = (uint8_t)(user_of[e0 + i] - first_user);
+    __syncthreads();
+    return ne;
+}
+
+// ---------------------------------------------------------------- tile_prepare: sort + windows + counts
+template <int TT, int TH>
+__global__ void __launch_bounds__(TH) tile_prepare_kernel(const int32_t *__restrict__ tile_first,
+                                                          const int32_t *__restrict__ tile_nusers,
+                                                          const uint8_t *__restrict__ active,
+                                                          const i64 *__restrict__ row_ptr, const int32_t *__restrict__ user_of,
+                                                          const double *__restrict__ m, const uint8_t *__restrict__ level,
+                                                          double *__restrict__ s_out, int32_t *__restrict__ pos_out,
+                                                          uint8_t *__restrict__ lev_out, int32_t *__restrict__ ub_out,
+                                                          int32_t *__restrict__ lb_out, int32_t *__restrict__ lo_out,
+                                                          int32_t *__restrict__ hi_out, int T) {
+    constexpr int CAP = TH * TE, SLOTS = CAP + TILE_MAX_USERS;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ TileShared<CAP> ts;
+    __shared__ int wagg[TH / 32 * TT];
+    __shared__ int wflag[TH / 32];
+    // dynamic layout: keys[CAP] f64 | C[T][SLOTS] i32 | idx[CAP] u16 | lev[CAP] u8
+    double *keys = reinterpret_cast<double *>(smraw);
+    int *C = reinterpret_cast<int *>(keys + CAP);
+    uint16_t *idx = reinterpret_cast<uint16_t *>(C + T * SLOTS);
+    uint8_t *slev = reinterpret_cast<uint8_t *>(idx + CAP);
+    const int tid = threadIdx.x;
+    const int first_user = tile_first[blockIdx.x], n_users = tile_nusers[blockIdx.x];
+    i64 e0;
+    const int ne = tile_setup<TH>(ts, first_user, n_users, row_ptr, user_of, active, e0);
+    if (ne == 0) return;
+    int np2 = 1;
+    while (np2 < ne) np2 <<= 1;
+    // composite key (user, score, index): padding sorts last
+    for (int i = tid; i < np2; i += TH) { keys[i] = i < ne ? m[e0 + i] : CUDART_INF; idx[i] = (uint16_t)i; }
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (np2 >> 1); t += TH) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const bool asc = (i & k) == 0;
+                const uint16_t ii = idx[i], ip = idx[p];
+                const int ui = ii < ne ? ts.ul[ii] : 255 + 1, up = ip < ne ? ts.ul[ip] : 255 + 1;
+                const double ki = keys[i], kp = keys[p];
+                const bool gt = (ui > up) || (ui == up && ((ki > kp) || (ki == kp && ii > ip)));
+                if (gt == asc) { keys[i] = kp; keys[p] = ki; idx[i] = ip; idx[p] = ii; }
+            }
+            __syncthreads();
+        }
+    }
+    // sorted outputs: users stay in place (the user is the major key), scores ascending inside each user
+    for (int i = tid; i < ne; i += TH) {
+        const int src = idx[i];
+        const uint8_t l = level[e0 + src];
+        slev[i] = l;
+        if (ts.uact[ts.ul[i]]) { s_out[e0 + i] = keys[i]; pos_out[e0 + i] = (int32_t)(e0 + src); lev_out[e0 + i] = l; }
+    }
+    __syncthreads();
+    // per-level exclusive prefix COUNTS
+    tile_level_scan<int, TT, TH>(ts, ne, T, C, wagg, wflag, [](int) { return 1; }, [&](int i) { return (int)slev[i]; });
+    // window pointers by binary search inside the user's segment, then the aggregated counters
+    for (int i = tid; i < ne; i += TH) {
+        const int u = ts.ul[i];
+        if (!ts.uact[u]) continue;
+        const int u0 = ts.ustart[u], n = ts.ustart[u + 1] - u0, x = i - u0;
+        const double *kk = keys + u0;
+        const double sj = kk[x];
+        const double hi = __dadd_rn(sj, 1.0), lo = __dadd_rn(sj, -1.0);
+        int a = x + 1, b = n;
+        while (a < b) { const int mid = (a + b) >> 1; if (kk[mid] <= hi) a = mid + 1; else b = mid; }
+        const int ub = a;
+        a = 0; b = x;
+        while (a < b) { const int mid = (a + b) >> 1; if (kk[mid] < lo) a = mid + 1; else b = mid; }
+        const int lb = a;
+        const int base = u0 + u, l = slev[i];
+        int chi = 0, clo = 0;
+        for (int t = 0; t < T; ++t) {
+            const int *Ct = C + t * SLOTS + base;
+            if (t > l) chi += Ct[ub];
+            else if (t < l) clo += Ct[n] - Ct[lb];
+        }
+        ub_out[e0 + i] = ub; lb_out[e0 + i] = lb; lo_out[e0 + i] = clo; hi_out[e0 + i] = chi;
+    }
+}
+
+// ---------------------------------------------------------------- tile_sweep
+// MODE 0: gradient coefficient (stream s)   c_j = 2 [ lo (s_j-1) + hi (s_j+1) - acc_j ]
+// MODE 1: Hv coefficient (stream b[pos])    c_j = 2 [ (lo+hi) b_j - acc_j ]
+//         acc_j = sum_{t<l_j} (S_t(n) - S_t(lb_j)) + sum_{t>l_j} S_t(ub_j)
+// MODE 2: per-user loss  sum_j [ hi s_j^2 - 2 s_j sum_{t>l_j} S1_t(ub_j) + sum_{t>l_j} S2_t(ub_j) ],
+//         S1 / S2 = per-level prefixes of (s-1) / (s-1)^2
+template <int MODE, int TT, int TH>
+__global__ void __launch_bounds__(TH) tile_sweep_kernel(const int32_t *__restrict__ tile_first,
+                                                        const int32_t *__restrict__ tile_nusers,
+                                                        const uint8_t *__restrict__ active,
+                                                        const i64 *__restrict__ row_ptr, const int32_t *__restrict__ user_of,
+                                                        const double *__restrict__ s_g, const int32_t *__restrict__ pos_g,
+                                                        const uint8_t *__restrict__ lev_g, const int32_t *__restrict__ ub_g,
+                                                        const int32_t *__restrict__ lb_g, const int32_t *__restrict__ lo_g,
+                                                        const int32_t *__restrict__ hi_g, const double *__restrict__ b_g,
+                                                        double *__restrict__ c_out, double *__restrict__ obj_user, int T) {
+    constexpr int CAP = TH * TE, SLOTS = CAP + TILE_MAX_USERS;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ TileShared<CAP> ts;
+    __shared__ double wagg[TH / 32 * TT];
+    __shared__ int wflag[TH / 32];
+    // dynamic layout: S[T][SLOTS] f64 | val[CAP] f64 | lev[CAP] u8
+    double *S = reinterpret_cast<double *>(smraw);
+    double *sval = S + T * SLOTS;
+    uint8_t *slev = reinterpret_cast<uint8_t *>(sval + CAP);
+    const int tid = threadIdx.x;
+    const int first_user = tile_first[blockIdx.x], n_users = tile_nusers[blockIdx.x];
+    i64 e0;
+    const int ne = tile_setup<TH>(ts, first_user, n_users, row_ptr, user_of, active, e0);
+    if (ne == 0) return;
+    for (int i = tid; i < ne; i += TH) {
+        slev[i] = lev_g[e0 + i];
+        if (MODE == 1) sval[i] = b_g[pos_g[e0 + i]];
+        else if (MODE == 0) sval[i] = s_g[e0 + i];
+        else sval[i] = s_g[e0 + i] - 1.0;
+    }
+    __syncthreads();
+    if (MODE != 2) {
+        tile_level_scan<double, TT, TH>(ts, ne, T, S, wagg, wflag, [&](int i) { return sval[i]; }, [&](int i) { return (int)slev[i]; });
+        for (int i = tid; i < ne; i += TH) {
+            const int u = ts.ul[i];
+            if (!ts.uact[u]) continue;
+            const int u0 = ts.ustart[u], n = ts.ustart[u + 1] - u0;
+            const int base = u0 + u, l = slev[i];
+            const int ub = ub_g[e0 + i], lb = lb_g[e0 + i];
+            double acc = 0.0;
+            for (int t = 0; t < T; ++t) {
+                const double *St = S + t * SLOTS + base;
+                if (t > l) acc += St[ub];
+                else if (t < l) acc += St[n] - St[lb];
+            }
+            const double lo = (double)lo_g[e0 + i], hi = (double)hi_g[e0 + i];
+            const double v = sval[i];
+            const double cc = MODE == 0 ? lo * (v - 1.0) + hi * (v + 1.0) - acc : (lo + hi) * v - acc;
+            c_out[pos_g[e0 + i]] = 2.0 * cc;
+        }
+    } else {
+        // pass A: S1 -> acc1 (kept in registers per owned striped element), pass B: S2 -> obj_j; pass C: user sums
+        double acc1[TE];
+        tile_level_scan<double, TT, TH>(ts, ne, T, S, wagg, wflag, [&](int i) { return sval[i]; }, [&](int i) { return (int)slev[i]; });
+#pragma unroll
+        for (int q = 0; q < TE; ++q) {
+            const int i = tid + q * TH;
+            double a = 0.0;
+            if (i < ne) {
+                const int u = ts.ul[i];
+                const int base = ts.ustart[u] + u, l = slev[i], ub = ub_g[e0 + i];
+                for (int t = l + 1; t < T; ++t) a += S[t * SLOTS + base + ub];
+            }
+            acc1[q] = a;
+        }
+        __syncthreads();
+        tile_level_scan<double, TT, TH>(ts, ne, T, S, wagg, wflag, [&](int i) { const double d = sval[i]; return d * d; },
+                                    [&](int i) { return (int)slev[i]; });
+        double objj[TE];
+#pragma unroll
+        for (int q = 0; q < TE; ++q) {
+            const int i = tid + q * TH;
+            double o = 0.0;
+            if (i < ne) {
+                const int u = ts.ul[i];
+                const int base = ts.ustart[u] + u, l = slev[i], ub = ub_g[e0 + i];
+                double a2 = 0.0;
+                for (int t = l + 1; t < T; ++t) a2 += S[t * SLOTS + base + ub];
+                const double sj = s_g[e0 + i];
+                o = (double)hi_g[e0 + i] * (sj * sj) - 2.0 * sj * acc1[q] + a2;
+            }
+            objj[q] = o;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < TE; ++q) { const int i = tid + q * TH; if (i < ne) sval[i] = objj[q]; }
+        __syncthreads();
+        // per-user totals: one more segmented scan with every element on level 0 (T = 1)
+        tile_level_scan<double, 1, TH>(ts, ne, 1, S, wagg, wflag, [&](int i) { return sval[i]; }, [](int) { return 0; });
+        for (int u = tid; u < n_users; u += TH) {
+            const int n = ts.ustart[u + 1] - ts.ustart[u];
+            if (n > 0 && ts.uact[u]) obj_user[first_user + u] = S[ts.ustart[u] + u + n];
+        }
+    }
+}
+
+static size_t prepare_smem(int T, int cap) { return (size_t)cap * 8 + (size_t)T * (cap + TILE_MAX_USERS) * 4 + (size_t)cap * 2 + cap; }
+static size_t sweep_smem(int T, int cap) { return (size_t)T * (cap + TILE_MAX_USERS) * 8 + (size_t)cap * 8 + cap; }
+
+template <typename K>
+static void set_smem(K kernel, size_t bytes) {
+    PCR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+// geo 0: small tiles (256 threads x 4 = TILE_CAP ratings), geo 1: large tiles (1024 threads x 4 = TILE_CAP_L ratings)
+void k_tile_prepare(Ctx &c, const DevCsr &X, int geo, const uint8_t *active, const double *m, SortedMeta &meta, int T) {
+    const TileList &L = X.tiles[geo];
+    if (L.n <= 0) return;
+    PCR_REQUIRE(T <= 8, "tile kernels support at most 8 rating levels");
+    const double bytes = (double)L.nnz * (8 + 1 + 4 + 8 + 4 + 1 + 16);
+#define PREP_ARGS L.first, L.nusers, active, X.row_ptr, X.user, m, X.level, meta.s, meta.pos, meta.lev, meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, T
+#define PREP_LAUNCH(TT, TH, NAME) { const size_t sm = prepare_smem(T, TH * TE); set_smem(tile_prepare_kernel<TT, TH>, sm); \
+        LAUNCH(c, NAME, bytes, (tile_prepare_kernel<TT, TH>), (unsigned)L.n, TH, sm, PREP_ARGS); }
+    if (geo == 0) { if (T <= 5) PREP_LAUNCH(5, 256, "tile_prepare") else PREP_LAUNCH(8, 256, "tile_prepare") }
+    else          { if (T <= 5) PREP_LAUNCH(5, 1024, "tile_prepare_L") else PREP_LAUNCH(8, 1024, "tile_prepare_L") }
+#undef PREP_LAUNCH
+#undef PREP_ARGS
+}
+
+void k_tile_sweep(Ctx &c, int mode, const DevCsr &X, int geo, const uint8_t *active, const SortedMeta &meta, const double *b,
+                  double *c_out, double *obj_user, int T) {
+    const TileList &L = X.tiles[geo];
+    if (L.n <= 0) return;
+    PCR_REQUIRE(T <= 8, "tile kernels support at most 8 rating levels");
+    const double per = mode == 2 ? (8 + 1 + 4 + 4 + 4) : (mode == 1 ? (8 + 4 + 1 + 16 + 8 + 8) : (8 + 4 + 1 + 16 + 8));
+    const double bytes = (double)L.nnz * per;
+    const unsigned grid = (unsigned)L.n;
+#define SW_ARGS L.first, L.nusers, active, X.row_ptr, X.user, meta.s, meta.pos, meta.lev, meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, b, c_out, obj_user, T
+#define SW_LAUNCH(MODE, TT, TH, NAME) { const size_t sm = sweep_smem(T, TH * TE); set_smem(tile_sweep_kernel<MODE, TT, TH>, sm); \
+        LAUNCH(c, NAME, bytes, (tile_sweep_kernel<MODE, TT, TH>), grid, TH, sm, SW_ARGS); }
+#define SW_MODE(MODE, NAME)                                                                                         \
+    if (geo == 0) { if (T <= 5) SW_LAUNCH(MODE, 5, 256, NAME) else SW_LAUNCH(MODE, 8, 256, NAME) }                   \
+    else          { if (T <= 5) SW_LAUNCH(MODE, 5, 1024, NAME "_L") else SW_LAUNCH(MODE, 8, 1024, NAME "_L") }
+    if (mode == 0) { SW_MODE(0, "tile_sweep_grad") }
+    else if (mode == 1) { SW_MODE(1, "tile_sweep_hv") }
+    else { SW_MODE(2, "tile_sweep_obj") }
+#undef SW_MODE
+#undef SW_LAUNCH
+#undef SW_ARGS
+}
+
+}  // namespace pcr

@@ -14,6 +14,8 @@ struct Ctx {               // what every launcher needs
 void k_expand_users(Ctx &c, const i64 *row_ptr, i64 d1, i64 nnz, int32_t *user_out);
 void k_levels(Ctx &c, const double *rating, i64 nnz, const i64 *table_dev, int T, uint8_t *level_out, int *bad_flag);
 void k_iota32(Ctx &c, int32_t *out, i64 n);
+// bpos[p*(nb+1)+j] = first CSC position of column p whose user id is >= j*block_users (users ascend inside a column)
+void k_csc_block_bounds(Ctx &c, const i64 *col_ptr, const int32_t *csc_user, i64 d2, int nb, i64 block_users, i64 *bpos);
 // CSC (by item) of a CSR: col_ptr[d2+1], csc2csr[nnz] (stable: users ascending inside an item), csc_user[nnz]
 void k_build_csc(Ctx &c, DevPool &pool, const int32_t *item, const int32_t *user, i64 nnz, i64 d2,
                  i64 *col_ptr, int32_t *csc2csr, int32_t *csc_user);
@@ -25,9 +27,13 @@ void k_heavy_sort(Ctx &c, DevPool &pool, void **temp, size_t *temp_bytes, const 
 // out[e] = P[prow[e]] . Q[qrow[e]]  (rows are ld-strided, ld % 4 == 0); skipped when active[prow[e]] == 0
 void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const int32_t *qrow, i64 n, int ld,
             const uint8_t *active, double *out, double bytes);
+// same as k_dots for the training set, user-major over row-sum units (P row in registers); false => use k_dots
+bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, const double *P, const double *Q,
+                  const int32_t *qrow, int ld, const uint8_t *active, double *out, double bytes);
 // out[seg] = lambda*x[seg] + sum_{e in seg} w[widx ? widx[e] : e] * M[ridx[e]]   (deterministic two-phase)
-void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, const i64 *seg_unit_ptr, i64 n_seg,
-              const int32_t *ridx, const int32_t *widx, const double *w, const double *M, int ld,
+// un_end == nullptr: unit u covers [un_start[u], un_start[u+1]); seg_unit_idx == nullptr: a segment's units are contiguous
+void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_end, i64 n_units, const i64 *seg_unit_ptr,
+              const int32_t *seg_unit_idx, i64 n_seg, const int32_t *ridx, const int32_t *widx, const double *w, const double *M, int ld,
               const uint8_t *active, double *partial, double lambda, const double *x, double *out,
               int zero_if_empty, double bytes);
 // per-user sort of scores (classes S and L, bitonic in shared memory); writes s / pos / lev
@@ -73,6 +79,13 @@ void k_u_ls_trial(Ctx &c, UState &s, const double *U, i64 d1, int ld, double ste
 void k_u_ls_check(Ctx &c, UState &s, i64 d1, int ld, double lambda, int last);
 void k_u_commit(Ctx &c, UState &s, double *U, i64 d1, int ld);
 void k_u_stats(Ctx &c, UState &s, const i64 *row_ptr, i64 d1, i64 *out8 /* device, 8 slots */);
+
+// ---------------------------------------------------------------- k_tiles.cu (tiles of consecutive small users)
+// geo 0: small tiles (users <= TILE_CAP ratings), geo 1: large tiles (TILE_CAP < len <= TILE_CAP_L)
+void k_tile_prepare(Ctx &c, const DevCsr &X, int geo, const uint8_t *active, const double *m, SortedMeta &meta, int T);
+// mode 0 gradient coefficient, 1 Hv coefficient (stream b), 2 per-user loss
+void k_tile_sweep(Ctx &c, int mode, const DevCsr &X, int geo, const uint8_t *active, const SortedMeta &meta, const double *b,
+                  double *c_out, double *obj_user, int T);
 
 // ---------------------------------------------------------------- k_pairs.cu (Primal-CR pair kernels, evaluation)
 // mode 0: gradient coefficient, 1: Hv coefficient (needs b), 2: objective partial per work item
