@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "sec_per_outer_iter_primalcrpp_k100_netflix_shape"
+_REAL_STDOUT = None
 
 
 def log(*a):
@@ -172,7 +173,7 @@ def main_reference(args):
         "cpu_baseline": {"value": value, "unit": "s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]},
         "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
     return 0
 
 
@@ -354,13 +355,18 @@ def main_ours(args):
         "roofline": roof, "cpu_baseline": cb,
         "objective": objs, "device_bytes": dev_bytes,
     }
-    print(json.dumps(line), flush=True)
+    _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 def main():
+    # libraries (NCCL's version banner, ...) may write to fd 1: keep the real stdout for the ONE JSON line only
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
