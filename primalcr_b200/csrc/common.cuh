@@ -95,7 +95,7 @@ struct DevPool {
     ~DevPool() { release(); }
 };
 
-struct TileList { int32_t *first = nullptr, *nusers = nullptr; i64 n = 0, nnz = 0; };
+struct TileList { int32_t *first = nullptr, *nusers = nullptr, *ne = nullptr; i64 *e0 = nullptr; i64 n = 0, nnz = 0; };
 
 // ------------------------------------------------------------------ a ratings set on the device (CSR by user)
 struct DevCsr {

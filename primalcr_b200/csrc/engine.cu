@@ -116,6 +116,7 @@ struct Engine {
         slots = pool.alloc<double>(32);
         red_partials = pool.alloc<double>(1024);
         us.counters = pool.alloc<int>(4);
+        ctx.ticket = pool.alloc<unsigned long long>(1);
         stats_dev = pool.alloc<i64>(8);
     }
     ~Engine() {
@@ -251,6 +252,13 @@ struct Engine {
             tb[gq].close();
             X.tiles[gq].n = (i64)tb[gq].first.size(); X.tiles[gq].nnz = tb[gq].nnz;
             X.tiles[gq].first = upload_vec(tb[gq].first); X.tiles[gq].nusers = upload_vec(tb[gq].num);
+            std::vector<i64> te0(tb[gq].first.size()); std::vector<int32_t> tne(tb[gq].first.size());
+            for (size_t q = 0; q < te0.size(); ++q) {
+                te0[q] = X.h_row_ptr[tb[gq].first[q]];
+                tne[q] = (int32_t)(X.h_row_ptr[(size_t)tb[gq].first[q] + tb[gq].num[q]] - te0[q]);
+            }
+            X.tiles[gq].e0 = upload_vec(te0); X.tiles[gq].ne = upload_vec(tne);
+            sync();
         }
         for (int q = 0; q < 3; ++q) { X.n_cls[q] = (int)cls[q].size(); X.cls_users[q] = upload_vec(cls[q]); }
         X.heavy_off = upload_vec(hoff); X.heavy_total = htot;

@@ -144,17 +144,21 @@ void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const
 // stays in registers, the 32 item indices of a batch are fetched with one coalesced load, and the NC 16-byte loads of
 // a rating's Q row are issued back to back before the first FMA (NC is a template parameter => fully unrolled).
 template <int G, int NC>
-__global__ void __launch_bounds__(256) dots_units_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
-                                                         i64 n_units, const double *__restrict__ P,
+__global__ void __launch_bounds__(256, 3) dots_units_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
+                                                         i64 n_units, unsigned long long *__restrict__ ticket,
+                                                         const double *__restrict__ P,
                                                          const double *__restrict__ Q, const int32_t *__restrict__ qrow,
                                                          int nch, int ld, const uint8_t *__restrict__ active,
                                                          double *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int lg = lane % G, grp = lane / G;
     constexpr int PW = 32 / G;
-    const i64 warp_global = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
-    const i64 nwarps = ((i64)gridDim.x * 256) >> 5;
-    for (i64 u = warp_global; u < n_units; u += nwarps) {
+    for (;;) {
+        // dynamic (work-stealing) unit scheduling: units differ in length, a ticket counter keeps every warp busy
+        unsigned long long tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1ull);
+        const i64 u = (i64)__shfl_sync(FULL, tk, 0);
+        if (u >= n_units) break;
         const int seg = un_seg[u];
         if (active && !active[seg]) continue;           // warp-uniform
         const i64 b = un_start[u], e = un_start[u + 1];
@@ -194,7 +198,8 @@ template <int G, int NC>
 static void launch_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, const double *P, const double *Q,
                               const int32_t *qrow, int nch, int ld, const uint8_t *active, double *out, double bytes) {
     const unsigned grid = resident_grid(dots_units_kernel<G, NC>, 256, 0, c.sms, (n_units + 7) / 8);
-    LAUNCH(c, active ? "dots_active" : "dots", bytes, (dots_units_kernel<G, NC>), grid, 256, 0, un_seg, un_start, n_units, P, Q, qrow,
+    PCR_CUDA(cudaMemsetAsync(c.ticket, 0, sizeof(unsigned long long), c.stream));
+    LAUNCH(c, active ? "dots_active" : "dots", bytes, (dots_units_kernel<G, NC>), grid, 256, 0, un_seg, un_start, n_units, c.ticket, P, Q, qrow,
            nch, ld, active, out);
 }
 
@@ -220,14 +225,17 @@ bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_unit
 template <int NCH>
 __global__ void __launch_bounds__(256) rowsum_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
                                                      const i64 *__restrict__ un_end,
-                                                     i64 n_units, const int32_t *__restrict__ ridx,
+                                                     i64 n_units, unsigned long long *__restrict__ ticket,
+                                                     const int32_t *__restrict__ ridx,
                                                      const int32_t *__restrict__ widx, const double *__restrict__ w,
                                                      const double *__restrict__ M, int ld, int nch,
                                                      const uint8_t *__restrict__ active, double *__restrict__ partial) {
     const int lane = threadIdx.x & 31;
-    const i64 warp_global = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
-    const i64 nwarps = ((i64)gridDim.x * 256) >> 5;
-    for (i64 u = warp_global; u < n_units; u += nwarps) {
+    for (;;) {
+        unsigned long long tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1ull);     // units are consumed in list order (user-block-major for the CSC)
+        const i64 u = (i64)__shfl_sync(FULL, tk, 0);
+        if (u >= n_units) break;
         const int seg = un_seg[u];
         if (active && !active[seg]) continue;           // warp-uniform
         const i64 b = un_start[u], e = un_end ? un_end[u] : un_start[u + 1];
@@ -305,11 +313,12 @@ void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_
             case 3: grid = resident_grid(rowsum_kernel<3>, 256, 0, c.sms, (n_units + 7) / 8); break;
             default: grid = resident_grid(rowsum_kernel<4>, 256, 0, c.sms, (n_units + 7) / 8); break;
         }
+        PCR_CUDA(cudaMemsetAsync(c.ticket, 0, sizeof(unsigned long long), c.stream));
         switch (NCH) {
-            case 1: LAUNCH(c, rs_name, bytes, rowsum_kernel<1>, grid, 256, 0, un_seg, un_start, un_end, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
-            case 2: LAUNCH(c, rs_name, bytes, rowsum_kernel<2>, grid, 256, 0, un_seg, un_start, un_end, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
-            case 3: LAUNCH(c, rs_name, bytes, rowsum_kernel<3>, grid, 256, 0, un_seg, un_start, un_end, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
-            default: LAUNCH(c, rs_name, bytes, rowsum_kernel<4>, grid, 256, 0, un_seg, un_start, un_end, n_units, ridx, widx, w, M, ld, nch, active, partial); break;
+            case 1: LAUNCH(c, rs_name, bytes, rowsum_kernel<1>, grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); break;
+            case 2: LAUNCH(c, rs_name, bytes, rowsum_kernel<2>, grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); break;
+            case 3: LAUNCH(c, rs_name, bytes, rowsum_kernel<3>, grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); break;
+            default: LAUNCH(c, rs_name, bytes, rowsum_kernel<4>, grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); break;
         }
     }
     if (n_seg > 0)

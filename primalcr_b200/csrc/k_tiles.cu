@@ -129,34 +129,29 @@ __device__ __forceinline__ void tile_level_scan(const TileShared<TH * TE> &ts, i
     __syncthreads();
 }
 
-// common tile set-up: user starts, active flags, element -> user map.  Returns ne (0 if nothing to do).
+// user starts + active flags of a tile.  Returns false (block-uniform) when no user of the tile takes part.
 template <int TH>
-__device__ __forceinline__ int tile_setup(TileShared<TH * TE> &ts, int first_user, int n_users, const i64 *__restrict__ row_ptr,
-                                          const int32_t *__restrict__ user_of, const uint8_t *__restrict__ active,
-                                          i64 &e0) {
+__device__ __forceinline__ bool tile_users(TileShared<TH * TE> &ts, int first_user, int n_users, i64 e0,
+                                           const i64 *__restrict__ row_ptr, const uint8_t *__restrict__ active) {
     const int tid = threadIdx.x;
-    e0 = row_ptr[first_user];
     int any = 0;
     for (int u = tid; u <= n_users; u += TH) {
-        ts.ustart[u] = (int)(row_ptr[first_user + u] - e0);
+        const i64 rp = row_ptr[first_user + u];
+        ts.ustart[u] = (int)(rp - e0);
         if (u < n_users) {
             const uint8_t a = active ? active[first_user + u] : (uint8_t)1;
             ts.uact[u] = a;
-            if (a && row_ptr[first_user + u + 1] > row_ptr[first_user + u]) any = 1;
+            if (a && row_ptr[first_user + u + 1] > rp) any = 1;
         }
     }
-    any = __syncthreads_or(any);
-    if (!any) return 0;
-    const int ne = ts.ustart[n_users];
-    for (int i = tid; i < ne; i += TH) ts.ul[i] = (uint8_t)(user_of[e0 + i] - first_user);
-    __syncthreads();
-    return ne;
+    return __syncthreads_or(any) != 0;
 }
 
 // ---------------------------------------------------------------- tile_prepare: sort + windows + counts
 template <int TT, int TH>
 __global__ void __launch_bounds__(TH) tile_prepare_kernel(const int32_t *__restrict__ tile_first,
                                                           const int32_t *__restrict__ tile_nusers,
+                                                          const i64 *__restrict__ tile_e0, const int32_t *__restrict__ tile_ne,
                                                           const uint8_t *__restrict__ active,
                                                           const i64 *__restrict__ row_ptr, const int32_t *__restrict__ user_of,
                                                           const double *__restrict__ m, const uint8_t *__restrict__ level,
@@ -169,40 +164,61 @@ __global__ void __launch_bounds__(TH) tile_prepare_kernel(const int32_t *__restr
     __shared__ TileShared<CAP> ts;
     __shared__ int wagg[TH / 32 * TT];
     __shared__ int wflag[TH / 32];
-    // dynamic layout: keys[CAP] f64 | C[T][SLOTS] i32 | idx[CAP] u16 | lev[CAP] u8
+    // dynamic layout: keys[CAP] f64 | C[T][SLOTS] i32 | tag[CAP] u32 | lev[CAP] u8 | lev0[CAP] u8
     double *keys = reinterpret_cast<double *>(smraw);
     int *C = reinterpret_cast<int *>(keys + CAP);
-    uint16_t *idx = reinterpret_cast<uint16_t *>(C + T * SLOTS);
-    uint8_t *slev = reinterpret_cast<uint8_t *>(idx + CAP);
+    uint32_t *tag = reinterpret_cast<uint32_t *>(C + T * SLOTS);
+    uint8_t *slev = reinterpret_cast<uint8_t *>(tag + CAP);
+    uint8_t *lev0 = slev + CAP;
     const int tid = threadIdx.x;
     const int first_user = tile_first[blockIdx.x], n_users = tile_nusers[blockIdx.x];
-    i64 e0;
-    const int ne = tile_setup<TH>(ts, first_user, n_users, row_ptr, user_of, active, e0);
-    if (ne == 0) return;
+    const i64 e0 = tile_e0[blockIdx.x];
+    const int ne = tile_ne[blockIdx.x];
+    bool users_done = false;
+    if (active) {                      // masked launch: find out first whether this tile has anything to do
+        if (!tile_users<TH>(ts, first_user, n_users, e0, row_ptr, active)) return;
+        users_done = true;
+    }
     int np2 = 1;
     while (np2 < ne) np2 <<= 1;
-    // composite key (user, score, index): padding sorts last
-    for (int i = tid; i < np2; i += TH) { keys[i] = i < ne ? m[e0 + i] : CUDART_INF; idx[i] = (uint16_t)i; }
+    // all global reads of the tile are issued here, back to back
+    double r_m[TE]; int r_u[TE]; uint8_t r_l[TE];
+#pragma unroll
+    for (int q = 0; q < TE; ++q) {
+        const int i = tid + q * TH;
+        r_m[q] = CUDART_INF; r_u[q] = 0xFFFF; r_l[q] = 0;
+        if (i < ne) { r_m[q] = m[e0 + i]; r_u[q] = user_of[e0 + i] - first_user; r_l[q] = level[e0 + i]; }
+    }
+    if (!users_done) tile_users<TH>(ts, first_user, n_users, e0, row_ptr, active);
+#pragma unroll
+    for (int q = 0; q < TE; ++q) {
+        const int i = tid + q * TH;
+        if (i < np2) {
+            keys[i] = r_m[q];
+            tag[i] = i < ne ? (((uint32_t)r_u[q] << 16) | (uint32_t)i) : 0xFFFFFFFFu;   // (user, index): padding last
+            if (i < ne) { ts.ul[i] = (uint8_t)r_u[q]; lev0[i] = r_l[q]; }
+        }
+    }
     __syncthreads();
+    // bitonic sort on the composite key (user, score, index)
     for (int k = 2; k <= np2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < (np2 >> 1); t += TH) {
                 const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const int p = i | j;
                 const bool asc = (i & k) == 0;
-                const uint16_t ii = idx[i], ip = idx[p];
-                const int ui = ii < ne ? ts.ul[ii] : 255 + 1, up = ip < ne ? ts.ul[ip] : 255 + 1;
+                const uint32_t ti = tag[i], tp = tag[p];
                 const double ki = keys[i], kp = keys[p];
-                const bool gt = (ui > up) || (ui == up && ((ki > kp) || (ki == kp && ii > ip)));
-                if (gt == asc) { keys[i] = kp; keys[p] = ki; idx[i] = ip; idx[p] = ii; }
+                const bool gt = ((ti >> 16) != (tp >> 16)) ? (ti > tp) : ((ki > kp) || (ki == kp && ti > tp));
+                if (gt == asc) { keys[i] = kp; keys[p] = ki; tag[i] = tp; tag[p] = ti; }
             }
             __syncthreads();
         }
     }
     // sorted outputs: users stay in place (the user is the major key), scores ascending inside each user
     for (int i = tid; i < ne; i += TH) {
-        const int src = idx[i];
-        const uint8_t l = level[e0 + src];
+        const int src = (int)(tag[i] & 0xFFFFu);
+        const uint8_t l = lev0[src];
         slev[i] = l;
         if (ts.uact[ts.ul[i]]) { s_out[e0 + i] = keys[i]; pos_out[e0 + i] = (int32_t)(e0 + src); lev_out[e0 + i] = l; }
     }
@@ -243,6 +259,7 @@ __global__ void __launch_bounds__(TH) tile_prepare_kernel(const int32_t *__restr
 template <int MODE, int TT, int TH>
 __global__ void __launch_bounds__(TH) tile_sweep_kernel(const int32_t *__restrict__ tile_first,
                                                         const int32_t *__restrict__ tile_nusers,
+                                                        const i64 *__restrict__ tile_e0, const int32_t *__restrict__ tile_ne,
                                                         const uint8_t *__restrict__ active,
                                                         const i64 *__restrict__ row_ptr, const int32_t *__restrict__ user_of,
                                                         const double *__restrict__ s_g, const int32_t *__restrict__ pos_g,
@@ -261,37 +278,65 @@ __global__ void __launch_bounds__(TH) tile_sweep_kernel(const int32_t *__restric
     uint8_t *slev = reinterpret_cast<uint8_t *>(sval + CAP);
     const int tid = threadIdx.x;
     const int first_user = tile_first[blockIdx.x], n_users = tile_nusers[blockIdx.x];
-    i64 e0;
-    const int ne = tile_setup<TH>(ts, first_user, n_users, row_ptr, user_of, active, e0);
-    if (ne == 0) return;
-    for (int i = tid; i < ne; i += TH) {
-        slev[i] = lev_g[e0 + i];
-        if (MODE == 1) sval[i] = b_g[pos_g[e0 + i]];
-        else if (MODE == 0) sval[i] = s_g[e0 + i];
-        else sval[i] = s_g[e0 + i] - 1.0;
+    const i64 e0 = tile_e0[blockIdx.x];
+    const int ne = tile_ne[blockIdx.x];
+    bool users_done = false;
+    if (active) {
+        if (!tile_users<TH>(ts, first_user, n_users, e0, row_ptr, active)) return;
+        users_done = true;
+    }
+    // every global read of the tile is issued up front (striped ownership i = tid + q*TH), the scan and the
+    // look-ups below then run from registers / shared memory only
+    int r_pos[TE], r_ub[TE], r_lb[TE], r_lo[TE], r_hi[TE], r_u[TE];
+    uint8_t r_l[TE];
+    double r_v[TE];
+#pragma unroll
+    for (int q = 0; q < TE; ++q) {
+        const int i = tid + q * TH;
+        r_pos[q] = 0; r_ub[q] = 0; r_lb[q] = 0; r_lo[q] = 0; r_hi[q] = 0; r_u[q] = 0; r_l[q] = 0; r_v[q] = 0.0;
+        if (i < ne) {
+            r_u[q] = user_of[e0 + i] - first_user;
+            r_l[q] = lev_g[e0 + i];
+            r_ub[q] = ub_g[e0 + i];
+            r_hi[q] = hi_g[e0 + i];
+            if (MODE != 2) { r_pos[q] = pos_g[e0 + i]; r_lb[q] = lb_g[e0 + i]; r_lo[q] = lo_g[e0 + i]; }
+            if (MODE != 1) r_v[q] = s_g[e0 + i];
+        }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int q = 0; q < TE; ++q) { const int i = tid + q * TH; if (i < ne) r_v[q] = b_g[r_pos[q]]; }
+    }
+    if (!users_done) tile_users<TH>(ts, first_user, n_users, e0, row_ptr, active);
+#pragma unroll
+    for (int q = 0; q < TE; ++q) {
+        const int i = tid + q * TH;
+        if (i < ne) { ts.ul[i] = (uint8_t)r_u[q]; slev[i] = r_l[q]; sval[i] = MODE == 2 ? r_v[q] - 1.0 : r_v[q]; }
     }
     __syncthreads();
     if (MODE != 2) {
         tile_level_scan<double, TT, TH>(ts, ne, T, S, wagg, wflag, [&](int i) { return sval[i]; }, [&](int i) { return (int)slev[i]; });
-        for (int i = tid; i < ne; i += TH) {
-            const int u = ts.ul[i];
+#pragma unroll
+        for (int q = 0; q < TE; ++q) {
+            const int i = tid + q * TH;
+            if (i >= ne) continue;
+            const int u = r_u[q];
             if (!ts.uact[u]) continue;
             const int u0 = ts.ustart[u], n = ts.ustart[u + 1] - u0;
-            const int base = u0 + u, l = slev[i];
-            const int ub = ub_g[e0 + i], lb = lb_g[e0 + i];
+            const int base = u0 + u, l = r_l[q];
             double acc = 0.0;
             for (int t = 0; t < T; ++t) {
                 const double *St = S + t * SLOTS + base;
-                if (t > l) acc += St[ub];
-                else if (t < l) acc += St[n] - St[lb];
+                if (t > l) acc += St[r_ub[q]];
+                else if (t < l) acc += St[n] - St[r_lb[q]];
             }
-            const double lo = (double)lo_g[e0 + i], hi = (double)hi_g[e0 + i];
-            const double v = sval[i];
+            const double lo = (double)r_lo[q], hi = (double)r_hi[q];
+            const double v = r_v[q];
             const double cc = MODE == 0 ? lo * (v - 1.0) + hi * (v + 1.0) - acc : (lo + hi) * v - acc;
-            c_out[pos_g[e0 + i]] = 2.0 * cc;
+            c_out[r_pos[q]] = 2.0 * cc;
         }
     } else {
-        // pass A: S1 -> acc1 (kept in registers per owned striped element), pass B: S2 -> obj_j; pass C: user sums
+        // pass A: S1 -> acc1, pass B: S2 -> obj_j, pass C: per-user sums
         double acc1[TE];
         tile_level_scan<double, TT, TH>(ts, ne, T, S, wagg, wflag, [&](int i) { return sval[i]; }, [&](int i) { return (int)slev[i]; });
 #pragma unroll
@@ -299,27 +344,27 @@ __global__ void __launch_bounds__(TH) tile_sweep_kernel(const int32_t *__restric
             const int i = tid + q * TH;
             double a = 0.0;
             if (i < ne) {
-                const int u = ts.ul[i];
-                const int base = ts.ustart[u] + u, l = slev[i], ub = ub_g[e0 + i];
-                for (int t = l + 1; t < T; ++t) a += S[t * SLOTS + base + ub];
+                const int u = r_u[q];
+                const int base = ts.ustart[u] + u;
+                for (int t = r_l[q] + 1; t < T; ++t) a += S[t * SLOTS + base + r_ub[q]];
             }
             acc1[q] = a;
         }
         __syncthreads();
         tile_level_scan<double, TT, TH>(ts, ne, T, S, wagg, wflag, [&](int i) { const double d = sval[i]; return d * d; },
-                                    [&](int i) { return (int)slev[i]; });
+                                        [&](int i) { return (int)slev[i]; });
         double objj[TE];
 #pragma unroll
         for (int q = 0; q < TE; ++q) {
             const int i = tid + q * TH;
             double o = 0.0;
             if (i < ne) {
-                const int u = ts.ul[i];
-                const int base = ts.ustart[u] + u, l = slev[i], ub = ub_g[e0 + i];
+                const int u = r_u[q];
+                const int base = ts.ustart[u] + u;
                 double a2 = 0.0;
-                for (int t = l + 1; t < T; ++t) a2 += S[t * SLOTS + base + ub];
-                const double sj = s_g[e0 + i];
-                o = (double)hi_g[e0 + i] * (sj * sj) - 2.0 * sj * acc1[q] + a2;
+                for (int t = r_l[q] + 1; t < T; ++t) a2 += S[t * SLOTS + base + r_ub[q]];
+                const double sj = r_v[q];
+                o = (double)r_hi[q] * (sj * sj) - 2.0 * sj * acc1[q] + a2;
             }
             objj[q] = o;
         }
@@ -336,7 +381,7 @@ __global__ void __launch_bounds__(TH) tile_sweep_kernel(const int32_t *__restric
     }
 }
 
-static size_t prepare_smem(int T, int cap) { return (size_t)cap * 8 + (size_t)T * (cap + TILE_MAX_USERS) * 4 + (size_t)cap * 2 + cap; }
+static size_t prepare_smem(int T, int cap) { return (size_t)cap * 8 + (size_t)T * (cap + TILE_MAX_USERS) * 4 + (size_t)cap * 4 + 2 * (size_t)cap; }
 static size_t sweep_smem(int T, int cap) { return (size_t)T * (cap + TILE_MAX_USERS) * 8 + (size_t)cap * 8 + cap; }
 
 template <typename K>
@@ -350,7 +395,7 @@ void k_tile_prepare(Ctx &c, const DevCsr &X, int geo, const uint8_t *active, con
     if (L.n <= 0) return;
     PCR_REQUIRE(T <= 8, "tile kernels support at most 8 rating levels");
     const double bytes = (double)L.nnz * (8 + 1 + 4 + 8 + 4 + 1 + 16);
-#define PREP_ARGS L.first, L.nusers, active, X.row_ptr, X.user, m, X.level, meta.s, meta.pos, meta.lev, meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, T
+#define PREP_ARGS L.first, L.nusers, L.e0, L.ne, active, X.row_ptr, X.user, m, X.level, meta.s, meta.pos, meta.lev, meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, T
 #define PREP_LAUNCH(TT, TH, NAME) { const size_t sm = prepare_smem(T, TH * TE); set_smem(tile_prepare_kernel<TT, TH>, sm); \
         LAUNCH(c, NAME, bytes, (tile_prepare_kernel<TT, TH>), (unsigned)L.n, TH, sm, PREP_ARGS); }
     if (geo == 0) { if (T <= 5) PREP_LAUNCH(5, 256, "tile_prepare") else PREP_LAUNCH(8, 256, "tile_prepare") }
@@ -367,7 +412,7 @@ void k_tile_sweep(Ctx &c, int mode, const DevCsr &X, int geo, const uint8_t *act
     const double per = mode == 2 ? (8 + 1 + 4 + 4 + 4) : (mode == 1 ? (8 + 4 + 1 + 16 + 8 + 8) : (8 + 4 + 1 + 16 + 8));
     const double bytes = (double)L.nnz * per;
     const unsigned grid = (unsigned)L.n;
-#define SW_ARGS L.first, L.nusers, active, X.row_ptr, X.user, meta.s, meta.pos, meta.lev, meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, b, c_out, obj_user, T
+#define SW_ARGS L.first, L.nusers, L.e0, L.ne, active, X.row_ptr, X.user, meta.s, meta.pos, meta.lev, meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, b, c_out, obj_user, T
 #define SW_LAUNCH(MODE, TT, TH, NAME) { const size_t sm = sweep_smem(T, TH * TE); set_smem(tile_sweep_kernel<MODE, TT, TH>, sm); \
         LAUNCH(c, NAME, bytes, (tile_sweep_kernel<MODE, TT, TH>), grid, TH, sm, SW_ARGS); }
 #define SW_MODE(MODE, NAME)                                                                                         \

@@ -8,6 +8,7 @@ struct Ctx {               // what every launcher needs
     cudaStream_t stream;
     Profiler *prof;
     int sms;               // SM count of the device (grid sizing)
+    unsigned long long *ticket;   // device counter for dynamically scheduled (work-stealing) kernels
 };
 
 // ---------------------------------------------------------------- k_setup.cu (one-time preprocessing)
