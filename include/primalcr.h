@@ -135,6 +135,21 @@ int     primalcr_profile_get(primalcr_engine *e, int idx, const char **name, dou
                              int64_t *launches, double *bytes);   /* bytes = algorithmic bytes moved     */
 int64_t primalcr_device_bytes(primalcr_engine *e);                /* device memory held by the engine    */
 
+/* ---- prediction: the loop of omp-pmf-predict pmf-predict.cpp:57-64 as one batch on the GPU ------------------------
+   out[t] = U[user[t]] . V[item[t]] for n (0-based) pairs; U is d1 x k, V is d2 x k row-major host arrays. */
+int primalcr_predict(const double *U, int64_t d1, const double *V, int64_t d2, int k, const int32_t *user,
+                     const int32_t *item, int64_t n, double *out, int device);
+
+/* ---- fast host loader for the reference's data directory (meta + ratings files): replaces load() util.cpp:6-25,
+   smat_t::load_from_iterator util.h:201-271 and testset_t::load util.h:360-371 (no GPU needed) ------------------ */
+typedef struct primalcr_dataset primalcr_dataset;
+int  primalcr_load_dir(const char *data_dir, int threads, primalcr_dataset **out);
+int  primalcr_dataset_info(const primalcr_dataset *ds, int64_t *d1, int64_t *d2, int64_t *nnz_train, int64_t *nnz_test);
+/* which = 0 training CSR (sorted by user, item), 1 test CSR (file order inside a user); pointers stay owned by ds */
+int  primalcr_dataset_csr(const primalcr_dataset *ds, int which, const int64_t **row_ptr, const int32_t **item,
+                          const double **rating);
+void primalcr_dataset_free(primalcr_dataset *ds);
+
 /* ---- host utilities (no GPU needed) -------------------------------------------------------------- */
 /* initial() util.cpp:80-93: default-seeded std::default_random_engine + normal_distribution<double>(0,1),
    row-major fill.  A fresh engine per call, so V equals the first d2 rows of U, as in the reference. */

@@ -50,7 +50,8 @@ SYMBOLS = [
     "primalcr_level_counts", "primalcr_num_levels", "primalcr_objective", "primalcr_grad_V", "primalcr_hv_V",
     "primalcr_grad_U", "primalcr_hv_U", "primalcr_stream", "primalcr_launch_count", "primalcr_profile_enable",
     "primalcr_profile_reset", "primalcr_profile_count", "primalcr_profile_get", "primalcr_device_bytes",
-    "primalcr_reference_init",
+    "primalcr_reference_init", "primalcr_predict", "primalcr_load_dir", "primalcr_dataset_info",
+    "primalcr_dataset_csr", "primalcr_dataset_free",
 ]
 
 _lib = None
@@ -111,6 +112,11 @@ def lib():
                                        C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.primalcr_device_bytes.argtypes = [vp]; L.primalcr_device_bytes.restype = C.c_int64
     L.primalcr_reference_init.argtypes = [f64p, C.c_int64, C.c_int64]; L.primalcr_reference_init.restype = None
+    L.primalcr_predict.argtypes = [f64p, C.c_int64, f64p, C.c_int64, C.c_int, i32p, i32p, C.c_int64, f64p, C.c_int]
+    L.primalcr_load_dir.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.primalcr_dataset_info.argtypes = [vp] + [C.POINTER(C.c_int64)] * 4
+    L.primalcr_dataset_csr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.primalcr_dataset_free.argtypes = [vp]; L.primalcr_dataset_free.restype = None
     _lib = L
     return L
 
@@ -128,6 +134,42 @@ def reference_init(n: int, k: int) -> np.ndarray:
     """initial() util.cpp:80-93 -- the default-seeded N(0,1) stream of the reference CLI (host code, libstdc++)."""
     out = np.empty((n, k), np.float64)
     lib().primalcr_reference_init(out.ctypes.data, n, k)
+    return out
+
+
+def load_dir(path: str, threads: int = 0):
+    """The library's parallel mmap loader for a reference data directory (host/loader.hpp) -> data.Dataset."""
+    from .data import Dataset
+    L = lib()
+    h = C.c_void_p()
+    rc = L.primalcr_load_dir(path.encode(), threads, C.byref(h))
+    if rc != 0:
+        raise PrimalCRError("primalcr error %d: %s" % (rc, L.primalcr_last_error().decode()))
+    try:
+        d1, d2, n0, n1 = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        L.primalcr_dataset_info(h, C.byref(d1), C.byref(d2), C.byref(n0), C.byref(n1))
+        out = []
+        for which, n in ((0, n0.value), (1, n1.value)):
+            rp, it, ra = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            L.primalcr_dataset_csr(h, which, C.byref(rp), C.byref(it), C.byref(ra))
+            row_ptr = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_int64)), (d1.value + 1,)).copy()
+            item = np.ctypeslib.as_array(C.cast(it, C.POINTER(C.c_int32)), (n,)).copy() if n else np.zeros(0, np.int32)
+            rating = np.ctypeslib.as_array(C.cast(ra, C.POINTER(C.c_double)), (n,)).copy() if n else np.zeros(0)
+            out.append(Ratings(d1.value, d2.value, row_ptr, item, rating))
+        return Dataset(out[0], out[1], name=os.path.basename(os.path.normpath(path)))
+    finally:
+        L.primalcr_dataset_free(h)
+
+
+def predict(U, V, users, items, device: int = 0) -> np.ndarray:
+    """omp-pmf-predict's loop (pmf-predict.cpp:57-64) as one GPU batch: out[t] = U[users[t]] . V[items[t]] (0-based)."""
+    U = np.ascontiguousarray(U, np.float64); V = np.ascontiguousarray(V, np.float64)
+    users = np.ascontiguousarray(users, np.int32); items = np.ascontiguousarray(items, np.int32)
+    out = np.empty(len(users))
+    rc = lib().primalcr_predict(U.ctypes.data, U.shape[0], V.ctypes.data, V.shape[0], U.shape[1], users.ctypes.data,
+                                items.ctypes.data, len(users), out.ctypes.data, device)
+    if rc != 0:
+        raise PrimalCRError("primalcr error %d: %s" % (rc, lib().primalcr_last_error().decode()))
     return out
 
 

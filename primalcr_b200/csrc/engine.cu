@@ -8,6 +8,7 @@
 // Arithmetic runs in the kernels of k_core.cu / k_pairs.cu.  There is no CPU implementation of any stage.
 #include "kernels.h"
 #include "../../include/primalcr.h"
+#include "../host/loader.hpp"
 
 #include <algorithm>
 #include <chrono>
@@ -1036,6 +1037,72 @@ int primalcr_profile_get(primalcr_engine *e, int idx, const char **name, double 
     API_END
 }
 int64_t primalcr_device_bytes(primalcr_engine *e) { return (e && e->impl) ? e->impl->pool.bytes : -1; }
+
+// ---- prediction (pmf-predict.cpp:57-64) ---------------------------------------------------------------
+int primalcr_predict(const double *U, int64_t d1, const double *V, int64_t d2, int k, const int32_t *user,
+                     const int32_t *item, int64_t n, double *out, int device) {
+    API_BEGIN
+    PCR_REQUIRE(U && V && (n == 0 || (user && item && out)) && k >= 1 && d1 >= 0 && d2 >= 0, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw pcr::Error(PRIMALCR_ECUDA, "no CUDA device available: libprimalcr_b200 has no CPU fallback");
+    for (int64_t t = 0; t < n; ++t)
+        PCR_REQUIRE(user[t] >= 0 && user[t] < d1 && item[t] >= 0 && item[t] < d2, "user/item id out of range");
+    PCR_CUDA(cudaSetDevice(device));
+    const int ld = pcr::ceil4(k);
+    pcr::DevPool pool; pcr::Profiler prof; pcr::Ctx ctx;
+    cudaDeviceProp prop; PCR_CUDA(cudaGetDeviceProperties(&prop, device));
+    cudaStream_t st; PCR_CUDA(cudaStreamCreate(&st));
+    ctx.stream = st; ctx.prof = &prof; ctx.sms = prop.multiProcessorCount; ctx.ticket = pool.alloc<unsigned long long>(1);
+    double *Uc = pool.alloc<double>((size_t)d1 * k), *Vc = pool.alloc<double>((size_t)d2 * k);
+    double *Ud = pool.alloc<double>((size_t)d1 * ld), *Vd = pool.alloc<double>((size_t)d2 * ld), *od = pool.alloc<double>((size_t)n);
+    int32_t *ud = pool.alloc<int32_t>((size_t)n), *id = pool.alloc<int32_t>((size_t)n);
+    PCR_CUDA(cudaMemcpyAsync(Uc, U, sizeof(double) * (size_t)d1 * k, cudaMemcpyHostToDevice, st));
+    PCR_CUDA(cudaMemcpyAsync(Vc, V, sizeof(double) * (size_t)d2 * k, cudaMemcpyHostToDevice, st));
+    PCR_CUDA(cudaMemcpyAsync(ud, user, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    PCR_CUDA(cudaMemcpyAsync(id, item, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    pcr::k_pad_copy(ctx, Uc, d1, k, ld, Ud); pcr::k_pad_copy(ctx, Vc, d2, k, ld, Vd);
+    pcr::k_dots(ctx, Ud, ud, Vd, id, n, ld, nullptr, od, 0.0);
+    if (n) PCR_CUDA(cudaMemcpyAsync(out, od, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    PCR_CUDA(cudaStreamSynchronize(st));
+    cudaStreamDestroy(st);
+    API_END
+}
+
+// ---- host loader ------------------------------------------------------------------------------------------
+struct primalcr_dataset { pcrhost::DataDir d; };
+
+int primalcr_load_dir(const char *data_dir, int threads, primalcr_dataset **out) {
+    API_BEGIN
+    PCR_REQUIRE(data_dir && out, "null argument");
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+    primalcr_dataset *ds = new primalcr_dataset;
+    try { ds->d = pcrhost::load_dir(data_dir); }
+    catch (const std::exception &ex) { delete ds; throw pcr::Error(PRIMALCR_EARG, ex.what()); }
+    *out = ds;
+    API_END
+}
+int primalcr_dataset_info(const primalcr_dataset *ds, int64_t *d1, int64_t *d2, int64_t *nnz_train, int64_t *nnz_test) {
+    API_BEGIN
+    PCR_REQUIRE(ds != nullptr, "null dataset");
+    if (d1) *d1 = ds->d.train.d1;
+    if (d2) *d2 = ds->d.train.d2;
+    if (nnz_train) *nnz_train = ds->d.train.nnz;
+    if (nnz_test) *nnz_test = ds->d.test.nnz;
+    API_END
+}
+int primalcr_dataset_csr(const primalcr_dataset *ds, int which, const int64_t **row_ptr, const int32_t **item, const double **rating) {
+    API_BEGIN
+    PCR_REQUIRE(ds != nullptr && (which == 0 || which == 1), "bad argument");
+    const pcrhost::Csr &c = which == 0 ? ds->d.train : ds->d.test;
+    if (row_ptr) *row_ptr = c.row_ptr.data();
+    if (item) *item = c.item.data();
+    if (rating) *rating = c.rating.data();
+    API_END
+}
+void primalcr_dataset_free(primalcr_dataset *ds) { delete ds; }
 
 // ---- host utilities -----------------------------------------------------------------------------------
 void primalcr_reference_init(double *out, int64_t n, int64_t k) {

@@ -317,3 +317,58 @@ def test_dropin_cli_reference_main_with_our_solver(tmp_path, solver):
     assert U.shape == (d1, k) and V.shape == (d2, k)
     assert rel(U, g["s%d_U" % solver]) < 1e-7 and rel(V, g["s%d_V" % solver]) < 1e-7
     assert os.path.exists(tmp_path / ("U.txt" if solver == 2 else "U%d.txt" % int(lam)))
+
+
+@pytest.mark.parametrize("solver", [2, 1])
+def test_own_cli_train_and_predict(tmp_path, solver):
+    """primalcr-train / primalcr-predict (our C++ host CLI: fast loader + C ABI) against the reference CLI's golden
+    stdout, model file, and the reference predictor's output format."""
+    import os
+    import subprocess
+    from primalcr_b200.data import Dataset, Ratings, load_model, write_reference_dir
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "primalcr_b200", "bin", "primalcr-train")
+    pexe = os.path.join(root, "primalcr_b200", "bin", "primalcr-predict")
+    assert os.path.exists(exe) and os.path.exists(pexe), "run __graft_entry__.build()"
+    g = np.load(os.path.join(root, "tests", "golden", "golden_tiny.npz"))
+    d1, d2, k, lam, iters = int(g["d1"]), int(g["d2"]), int(g["k"]), float(g["lam"]), int(g["iters"])
+    ds = Dataset(Ratings(d1, d2, g["row_ptr"], g["item"], g["rating"]), Ratings(d1, d2, g["t_row_ptr"], g["t_item"], g["t_rating"]))
+    write_reference_dir(str(tmp_path / "data"), ds)
+    out = subprocess.run([exe, "-s", str(solver), "-k", str(k), "-l", str(lam), "-t", str(iters), "-p", "1", "-n", "2",
+                          str(tmp_path / "data"), str(tmp_path / "model")], cwd=tmp_path, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    ref_lines = str(g["s%d_stdout" % solver]).splitlines()
+    ours = out.stdout.splitlines()
+    assert ours[0] == ref_lines[0] and ours[1] == ref_lines[1] and ours[2] == ref_lines[2]     # rank / rows+cols / nnz header
+    pick = lambda ls: [l for l in ls if l.startswith(("Iter", "(Training)", "(Testing)"))]
+    for a, b in zip(pick(ours), pick(ref_lines)):
+        ta, tb = a.split(), b.split()
+        assert ta[0] == tb[0]
+        if ta[0] == "Iter":
+            assert abs(float(ta[-1]) - float(tb[-1])) <= 2e-5 * abs(float(tb[-1]))
+        else:
+            assert abs(float(ta[4]) - float(tb[4])) < 2e-5 and abs(float(ta[-1]) - float(tb[-1])) < NDCG_TOL
+    assert len(pick(ours)) == len(pick(ref_lines))
+    U, V = load_model(str(tmp_path / "model"))
+    assert rel(U, g["s%d_U" % solver]) < 1e-7 and rel(V, g["s%d_V" % solver]) < 1e-7
+    txt = np.loadtxt(tmp_path / ("U.txt" if solver == 2 else "U%d.txt" % int(lam)))
+    assert txt.shape == (d1, k) and np.allclose(txt, U, rtol=2e-5, atol=1e-12)
+    # predict: same "%lf" lines as omp-pmf-predict
+    write = tmp_path / "data" / "test.ratings"
+    r = subprocess.run([pexe, str(write), str(tmp_path / "model"), str(tmp_path / "pred")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    pred = np.loadtxt(tmp_path / "pred")
+    T = ds.test
+    want = np.einsum("ij,ij->i", U[T.users()], V[T.item])
+    assert np.allclose(pred, want, atol=1e-6)
+    assert np.allclose(api.predict(U, V, T.users(), T.item), want, rtol=1e-13, atol=1e-13)
+    refp = ob.ref_cli("omp-pmf-predict")
+    if refp:
+        subprocess.run([refp, str(write), str(tmp_path / "model"), str(tmp_path / "pred_ref")], check=True)
+        assert open(tmp_path / "pred").read() == open(tmp_path / "pred_ref").read()        # byte-identical output file
+    # warm start (-w): one more iteration from the saved model continues the same trajectory
+    out2 = subprocess.run([exe, "-s", str(solver), "-k", str(k), "-l", str(lam), "-t", "1", "-p", "0", "-w", str(tmp_path / "model"),
+                           str(tmp_path / "data"), str(tmp_path / "model2")], cwd=tmp_path, capture_output=True, text=True)
+    assert out2.returncode == 0, out2.stderr
+    o = [float(l.split()[-1]) for l in out2.stdout.splitlines() if l.startswith("Iter ")]
+    assert abs(o[0] - float(g["s%d_obj" % solver][iters])) <= 2e-5 * o[0] and o[1] < o[0]

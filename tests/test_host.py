@@ -109,3 +109,36 @@ def test_synthetic_generator_is_deterministic_and_well_formed():
         assert np.all(np.diff(it) > 0)                              # ascending, no duplicates (util.h:240)
     pl = synth_dataset("powerlaw", scale=0.0005)
     assert pl.train.lens().max() <= 100_000
+
+
+def test_fast_loader_matches_python_reader(tmp_path):
+    """host/loader.hpp (parallel mmap parser, counting sort by user) == the Python mirror of the reference loader,
+    on a shuffled training file (the reference sorts by (user, item), util.h:240) and a grouped test file."""
+    ds = dataset("tiny")
+    d = tmp_path / "d"; write_reference_dir(str(d), ds)
+    lines = open(d / "training.ratings").read().splitlines()
+    np.random.default_rng(3).shuffle(lines)
+    open(d / "training.ratings", "w").write("\n".join(lines) + "\n")
+    a = api.load_dir(str(d), 4)
+    b = read_reference_dir(str(d))
+    for x, y in ((a.train, b.train), (a.test, b.test)):
+        assert x.d1 == y.d1 and x.d2 == y.d2
+        assert np.array_equal(x.row_ptr, y.row_ptr) and np.array_equal(x.item, y.item) and np.array_equal(x.rating, y.rating)
+    assert np.array_equal(a.train.item, ds.train.item) and np.array_equal(a.train.rating, ds.train.rating)
+
+
+def test_fast_loader_real_valued_and_errors(tmp_path):
+    d = tmp_path / "d"; d.mkdir()
+    (d / "meta").write_text("3 4\n5 tr.txt\n2 te.txt\n")
+    (d / "tr.txt").write_text("3 1 -0.5\n1 4 2.25e0\n1 2 1e-3\n2 3 4\n3 4 0.0576852\n")
+    (d / "te.txt").write_text("1 1 5\n3 2 1.5\n")
+    a = api.load_dir(str(d), 2)
+    assert a.train.row_ptr.tolist() == [0, 2, 3, 5] and a.train.item.tolist() == [1, 3, 2, 0, 3]
+    assert a.train.rating.tolist() == [1e-3, 2.25, 4.0, -0.5, 0.0576852]
+    assert a.test.row_ptr.tolist() == [0, 1, 1, 2] and a.test.rating.tolist() == [5.0, 1.5]
+    with pytest.raises(api.PrimalCRError):
+        api.load_dir(str(tmp_path / "missing"))
+    (d / "tr.txt").write_text("9 1 1\n")
+    (d / "meta").write_text("3 4\n1 tr.txt\n")
+    with pytest.raises(api.PrimalCRError, match="out of range"):
+        api.load_dir(str(d))
