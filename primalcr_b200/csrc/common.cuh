@@ -129,6 +129,12 @@ struct SortedMeta {          // per rating, in (user, ascending score) order
     uint8_t *lev = nullptr;  // its level
     int32_t *ub = nullptr, *lb = nullptr;      // window pointers (local to the user)
     int32_t *cnt_lo = nullptr, *cnt_hi = nullptr;
+    // level-major copy for the users served by tiles: per rating in (user, level, ascending score) order
+    double *lm_s = nullptr; int32_t *lm_pos = nullptr; uint8_t *lm_lev = nullptr;
+    int32_t *lm_lo = nullptr, *lm_hi = nullptr;
+    uint16_t *lm_idx = nullptr;   // [(T-1) planes][nnz]: rank (inside the user, level-major) of the window end in every OTHER level
+    uint16_t *ulev = nullptr;     // [d1][8] ratings per level of every user
+    i64 nnz = 0;                  // plane stride of lm_idx
 };
 
 static const int TILE_CAP = 1024;        // ratings per tile of consecutive users (k_tiles.cu)

@@ -326,6 +326,15 @@ struct Engine {
         meta.lev = pool.alloc<uint8_t>((size_t)nnz);
         meta.ub = pool.alloc<int32_t>((size_t)nnz); meta.lb = pool.alloc<int32_t>((size_t)nnz);
         meta.cnt_lo = pool.alloc<int32_t>((size_t)nnz); meta.cnt_hi = pool.alloc<int32_t>((size_t)nnz);
+        meta.nnz = nnz;
+        if (use_tiles && getenv("PRIMALCR_NO_LM") == nullptr) {     // level-major copy for the tile users
+            meta.lm_s = pool.alloc<double>((size_t)nnz); meta.lm_pos = pool.alloc<int32_t>((size_t)nnz);
+            meta.lm_lev = pool.alloc<uint8_t>((size_t)nnz);
+            meta.lm_lo = pool.alloc<int32_t>((size_t)nnz); meta.lm_hi = pool.alloc<int32_t>((size_t)nnz);
+            meta.lm_idx = pool.alloc<uint16_t>((size_t)nnz * (size_t)std::max(T - 1, 1));
+            meta.ulev = pool.alloc<uint16_t>((size_t)d1 * 8);
+            PCR_CUDA(cudaMemsetAsync(meta.ulev, 0, sizeof(uint16_t) * (size_t)d1 * 8, stream));
+        }
         iota = pool.alloc<int32_t>((size_t)nnz);
         k_iota32(ctx, iota, nnz);
         const size_t vn = (size_t)d2 * ld, un = (size_t)d1 * ld;

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(TH) tile_prepare_kernel(const int32_t *__restr
                                                           double *__restrict__ s_out, int32_t *__restrict__ pos_out,
                                                           uint8_t *__restrict__ lev_out, int32_t *__restrict__ ub_out,
                                                           int32_t *__restrict__ lb_out, int32_t *__restrict__ lo_out,
-                                                          int32_t *__restrict__ hi_out, int T) {
+                                                          int32_t *__restrict__ hi_out, int T, SortedMeta lm) {
     constexpr int CAP = TH * TE, SLOTS = CAP + TILE_MAX_USERS;
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ TileShared<CAP> ts;
@@ -247,6 +247,162 @@ __global__ void __launch_bounds__(TH) tile_prepare_kernel(const int32_t *__restr
             else if (t < l) clo += Ct[n] - Ct[lb];
         }
         ub_out[e0 + i] = ub; lb_out[e0 + i] = lb; lo_out[e0 + i] = clo; hi_out[e0 + i] = chi;
+        // level-major copy: rank of this rating in (level, score) order inside its user, and for every OTHER level t the
+        // rank where its window ends: B_t + C_t(ub) above, B_t + C_t(lb) below  (B_t = first rank of level t)
+        if (lm.lm_s != nullptr) {
+            int run = 0, r = 0;
+            uint16_t other[TT];
+#pragma unroll
+            for (int t = 0; t < TT; ++t) {
+                other[t] = 0;
+                if (t < T) {
+                    const int *Ct = C + t * SLOTS + base;
+                    if (t == l) r = run + Ct[x];
+                    else other[t] = (uint16_t)(run + (t > l ? Ct[ub] : Ct[lb]));
+                    run += Ct[n];
+                }
+            }
+            const i64 gi = e0 + u0 + r;
+            lm.lm_s[gi] = sj; lm.lm_pos[gi] = (int32_t)(e0 + (int)(tag[i] & 0xFFFFu)); lm.lm_lev[gi] = (uint8_t)l;
+            lm.lm_lo[gi] = clo; lm.lm_hi[gi] = chi;
+#pragma unroll
+            for (int t = 0; t < TT; ++t)
+                if (t < T && t != l) lm.lm_idx[(i64)(t < l ? t : t - 1) * lm.nnz + gi] = other[t];
+        }
+    }
+    if (lm.ulev != nullptr) {
+        for (int w = tid; w < n_users * T; w += TH) {
+            const int u = w / T, t = w - u * T;
+            const int n = ts.ustart[u + 1] - ts.ustart[u];
+            if (ts.uact[u]) lm.ulev[(i64)(first_user + u) * 8 + t] = (uint16_t)(n > 0 ? C[t * SLOTS + ts.ustart[u] + u + n] : 0);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- tile_lm_sweep: the sweeps on the level-major copy
+// In (user, level, score) order the ratings of one level form a block, so every per-level prefix S_t(x) is a difference
+// of ONE running prefix G over the user: S_t(x) = G[B_t + C_t(x)] - G[B_t].  A scalar segmented scan replaces the
+// T-vector scan of tile_sweep_kernel, and the look-up positions B_t + C_t(ub|lb) were stored by tile_prepare:
+//   acc_j = sum_{t>l} (G[idx_t] - G[B_t]) + sum_{t<l} (G[B_{t+1}] - G[idx_t]) = K_u[l] + sum_{t>l} G[idx_t] - sum_{t<l} G[idx_t]
+template <int MODE, int TT, int TH>
+__global__ void __launch_bounds__(TH) tile_lm_sweep_kernel(const int32_t *__restrict__ tile_first,
+                                                           const int32_t *__restrict__ tile_nusers,
+                                                           const i64 *__restrict__ tile_e0, const int32_t *__restrict__ tile_ne,
+                                                           const uint8_t *__restrict__ active,
+                                                           const i64 *__restrict__ row_ptr, const int32_t *__restrict__ user_of,
+                                                           SortedMeta lm, const double *__restrict__ b_g,
+                                                           double *__restrict__ c_out, double *__restrict__ obj_user, int T) {
+    constexpr int CAP = TH * TE, SLOTS = CAP + TILE_MAX_USERS;
+    __shared__ TileShared<CAP> ts;
+    __shared__ double wagg[TH / 32];
+    __shared__ int wflag[TH / 32];
+    extern __shared__ __align__(16) unsigned char smraw[];
+    // dynamic layout: G[SLOTS] | sval[CAP] | G2[SLOTS] (objective only)
+    double *G = reinterpret_cast<double *>(smraw);
+    double *sval = G + SLOTS;
+    double *G2 = sval + CAP;
+    __shared__ double Kt[TILE_MAX_USERS * TT], Kt2[MODE == 2 ? TILE_MAX_USERS * TT : 1];
+    __shared__ uint16_t Bt[TILE_MAX_USERS * (TT + 1)];
+    const int tid = threadIdx.x;
+    const int first_user = tile_first[blockIdx.x], n_users = tile_nusers[blockIdx.x];
+    const i64 e0 = tile_e0[blockIdx.x];
+    const int ne = tile_ne[blockIdx.x];
+    bool users_done = false;
+    if (active) {
+        if (!tile_users<TH>(ts, first_user, n_users, e0, row_ptr, active)) return;
+        users_done = true;
+    }
+    int r_pos[TE], r_lo[TE], r_hi[TE], r_u[TE];
+    uint8_t r_l[TE];
+    uint16_t r_idx[TE][TT - 1];
+    double r_v[TE];
+#pragma unroll
+    for (int q = 0; q < TE; ++q) {
+        const int i = tid + q * TH;
+        r_pos[q] = 0; r_lo[q] = 0; r_hi[q] = 0; r_u[q] = 0; r_l[q] = 0; r_v[q] = 0.0;
+#pragma unroll
+        for (int t = 0; t < TT - 1; ++t) r_idx[q][t] = 0;
+        if (i < ne) {
+            r_u[q] = user_of[e0 + i] - first_user;
+            r_l[q] = lm.lm_lev[e0 + i];
+            r_hi[q] = lm.lm_hi[e0 + i];
+            if (MODE != 2) { r_pos[q] = lm.lm_pos[e0 + i]; r_lo[q] = lm.lm_lo[e0 + i]; }
+            if (MODE != 1) r_v[q] = lm.lm_s[e0 + i];
+#pragma unroll
+            for (int t = 0; t < TT - 1; ++t) if (t < T - 1) r_idx[q][t] = lm.lm_idx[(i64)t * lm.nnz + e0 + i];
+        }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int q = 0; q < TE; ++q) { const int i = tid + q * TH; if (i < ne) r_v[q] = b_g[r_pos[q]]; }
+    }
+    if (!users_done) tile_users<TH>(ts, first_user, n_users, e0, row_ptr, active);
+    // block starts of every user's levels (ranks inside the user)
+    for (int u = tid; u < n_users; u += TH) {
+        int run = 0;
+        for (int t = 0; t < T; ++t) { Bt[u * (TT + 1) + t] = (uint16_t)run; run += lm.ulev[(i64)(first_user + u) * 8 + t]; }
+        Bt[u * (TT + 1) + T] = (uint16_t)run;
+    }
+#pragma unroll
+    for (int q = 0; q < TE; ++q) {
+        const int i = tid + q * TH;
+        if (i < ne) { ts.ul[i] = (uint8_t)r_u[q]; sval[i] = MODE == 2 ? r_v[q] - 1.0 : r_v[q]; }
+    }
+    __syncthreads();
+    tile_level_scan<double, 1, TH>(ts, ne, 1, G, wagg, wflag, [&](int i) { return sval[i]; }, [](int) { return 0; });
+    if (MODE == 2)
+        tile_level_scan<double, 1, TH>(ts, ne, 1, G2, wagg, wflag, [&](int i) { const double d = sval[i]; return d * d; }, [](int) { return 0; });
+    // per-user constants K_u[l]
+    for (int w = tid; w < n_users * T; w += TH) {
+        const int u = w / T, l = w - u * T;
+        const int base = ts.ustart[u] + u;
+        const uint16_t *B = Bt + u * (TT + 1);
+        double k1 = 0.0, k2 = 0.0;
+        for (int t = 0; t < T; ++t) {
+            if (t > l) { k1 -= G[base + B[t]]; if (MODE == 2) k2 -= G2[base + B[t]]; }
+            else if (t < l && MODE != 2) k1 += G[base + B[t + 1]];
+        }
+        Kt[u * TT + l] = k1;
+        if (MODE == 2) Kt2[u * TT + l] = k2;
+    }
+    __syncthreads();
+    double objj[TE];
+#pragma unroll
+    for (int q = 0; q < TE; ++q) {
+        const int i = tid + q * TH;
+        objj[q] = 0.0;
+        if (i >= ne) continue;
+        const int u = r_u[q];
+        if (!ts.uact[u]) continue;
+        const int base = ts.ustart[u] + u, l = r_l[q];
+        double acc = Kt[u * TT + l], acc2 = MODE == 2 ? Kt2[u * TT + l] : 0.0;
+#pragma unroll
+        for (int t = 0; t < TT - 1; ++t) {
+            if (t < T - 1) {
+                const int at = base + r_idx[q][t];
+                if (t >= l) { acc += G[at]; if (MODE == 2) acc2 += G2[at]; }      // other level t+1 > l
+                else if (MODE != 2) acc -= G[at];                                    // other level t < l
+            }
+        }
+        const double v = r_v[q];
+        if (MODE == 2) {
+            objj[q] = (double)r_hi[q] * (v * v) - 2.0 * v * acc + acc2;
+        } else {
+            const double lo = (double)r_lo[q], hi = (double)r_hi[q];
+            const double cc = MODE == 0 ? lo * (v - 1.0) + hi * (v + 1.0) - acc : (lo + hi) * v - acc;
+            c_out[r_pos[q]] = 2.0 * cc;
+        }
+    }
+    if (MODE == 2) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < TE; ++q) { const int i = tid + q * TH; if (i < ne) sval[i] = objj[q]; }
+        __syncthreads();
+        tile_level_scan<double, 1, TH>(ts, ne, 1, G, wagg, wflag, [&](int i) { return sval[i]; }, [](int) { return 0; });
+        for (int u = tid; u < n_users; u += TH) {
+            const int n = ts.ustart[u + 1] - ts.ustart[u];
+            if (n > 0 && ts.uact[u]) obj_user[first_user + u] = G[ts.ustart[u] + u + n];
+        }
     }
 }
 
@@ -395,7 +551,7 @@ void k_tile_prepare(Ctx &c, const DevCsr &X, int geo, const uint8_t *active, con
     if (L.n <= 0) return;
     PCR_REQUIRE(T <= 8, "tile kernels support at most 8 rating levels");
     const double bytes = (double)L.nnz * (8 + 1 + 4 + 8 + 4 + 1 + 16);
-#define PREP_ARGS L.first, L.nusers, L.e0, L.ne, active, X.row_ptr, X.user, m, X.level, meta.s, meta.pos, meta.lev, meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, T
+#define PREP_ARGS L.first, L.nusers, L.e0, L.ne, active, X.row_ptr, X.user, m, X.level, meta.s, meta.pos, meta.lev, meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, T, meta
 #define PREP_LAUNCH(TT, TH, NAME) { const size_t sm = prepare_smem(T, TH * TE); set_smem(tile_prepare_kernel<TT, TH>, sm); \
         LAUNCH(c, NAME, bytes, (tile_prepare_kernel<TT, TH>), (unsigned)L.n, TH, sm, PREP_ARGS); }
     if (geo == 0) { if (T <= 5) PREP_LAUNCH(5, 256, "tile_prepare") else PREP_LAUNCH(8, 256, "tile_prepare") }
@@ -412,6 +568,21 @@ void k_tile_sweep(Ctx &c, int mode, const DevCsr &X, int geo, const uint8_t *act
     const double per = mode == 2 ? (8 + 1 + 4 + 4 + 4) : (mode == 1 ? (8 + 4 + 1 + 16 + 8 + 8) : (8 + 4 + 1 + 16 + 8));
     const double bytes = (double)L.nnz * per;
     const unsigned grid = (unsigned)L.n;
+    if (meta.lm_s != nullptr) {          // level-major fast path (scalar segmented scan)
+#define LM_ARGS L.first, L.nusers, L.e0, L.ne, active, X.row_ptr, X.user, meta, b, c_out, obj_user, T
+#define LM_LAUNCH(MODE, TT, TH, NAME) { const size_t sm = ((size_t)(TH * TE + TILE_MAX_USERS) * (MODE == 2 ? 2 : 1) + TH * TE) * 8; \
+        set_smem(tile_lm_sweep_kernel<MODE, TT, TH>, sm); LAUNCH(c, NAME, bytes, (tile_lm_sweep_kernel<MODE, TT, TH>), grid, TH, sm, LM_ARGS); }
+#define LM_MODE(MODE, NAME)                                                                                         \
+        if (geo == 0) { if (T <= 5) { LM_LAUNCH(MODE, 5, 256, NAME) } else { LM_LAUNCH(MODE, 8, 256, NAME) } }        \
+        else          { LM_LAUNCH(MODE, 5, 1024, NAME "_L") }
+        if (mode == 0) { LM_MODE(0, "lm_sweep_grad") }
+        else if (mode == 1) { LM_MODE(1, "lm_sweep_hv") }
+        else { LM_MODE(2, "lm_sweep_obj") }
+#undef LM_MODE
+#undef LM_LAUNCH
+#undef LM_ARGS
+        return;
+    }
 #define SW_ARGS L.first, L.nusers, L.e0, L.ne, active, X.row_ptr, X.user, meta.s, meta.pos, meta.lev, meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, b, c_out, obj_user, T
 #define SW_LAUNCH(MODE, TT, TH, NAME) { const size_t sm = sweep_smem(T, TH * TE); set_smem(tile_sweep_kernel<MODE, TT, TH>, sm); \
         LAUNCH(c, NAME, bytes, (tile_sweep_kernel<MODE, TT, TH>), grid, TH, sm, SW_ARGS); }
