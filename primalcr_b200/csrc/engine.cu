@@ -48,7 +48,8 @@ static NcclApi g_nccl;
 
 static thread_local std::string g_last_error;
 
-static int ceil4(int k) { return (k + 3) & ~3; }
+// leading dimension of every factor-shaped array: rows start on 128-byte lines (a 128-byte row chunk never straddles two)
+static int ceil4(int k) { return (k + 15) & ~15; }
 
 struct Engine {
     primalcr_config cfg;
@@ -286,7 +287,7 @@ struct Engine {
         // (users ascend inside a column, so a column's entries of one block are contiguous).
         {
             const double u_bytes = (double)d1 * ld * 8.0;
-            const double blk_bytes = getenv("PRIMALCR_UBLOCK_MB") ? atof(getenv("PRIMALCR_UBLOCK_MB")) * 1e6 : 40e6;
+            const double blk_bytes = getenv("PRIMALCR_UBLOCK_MB") ? atof(getenv("PRIMALCR_UBLOCK_MB")) * 1e6 : 24e6;
             int nb = (int)std::ceil(u_bytes / blk_bytes);
             if (nb < 1) nb = 1;
             if (nb > 64) nb = 64;
@@ -447,8 +448,8 @@ struct Engine {
     // out[e] = P[user(e)] . Q[item(e)] over the training set
     void train_dots(const double *P, const double *Q, double *out, const uint8_t *active) {
         const double bytes = active ? 0.0 : pass_bytes(X.nnz, d1);
-        if (!k_dots_units(ctx, X.un_seg, X.un_start, X.n_units, P, Q, X.item, ld, active, out, bytes))
-            k_dots(ctx, P, X.user, Q, X.item, X.nnz, ld, active, out, bytes);
+        if (!k_dots_units(ctx, X.un_seg, X.un_start, X.n_units, P, Q, X.item, ld, k, active, out, bytes))
+            k_dots(ctx, P, X.user, Q, X.item, X.nnz, ld, k, active, out, bytes);
     }
     // get_sorted_mm + window pointers for every (active) user
     void prepare(const double *sc, const uint8_t *active) {
@@ -498,10 +499,10 @@ struct Engine {
         const double bytes = pass_bytes(X.nnz, d2);
         if (world <= 1) {
             k_rowsum(ctx, cu_seg, cu_start, cu_end, n_cunits, col_unit_ptr, col_unit_idx, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
-                     cfg.lambda, x, out, 0, bytes);
+                     cfg.lambda, x, out, 0, bytes, k);
         } else {
             k_rowsum(ctx, cu_seg, cu_start, cu_end, n_cunits, col_unit_ptr, col_unit_idx, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
-                     0.0, nullptr, out, 0, bytes);
+                     0.0, nullptr, out, 0, bytes, k);
             allreduce(out, (size_t)d2 * ld);
             k_axpby(ctx, out, 1.0, out, cfg.lambda, x, d2 * ld);
         }
@@ -509,7 +510,7 @@ struct Engine {
     // out[i] = lambda*x[i] + sum over user i of cbuf[e] * V[item(e)]   (U-side gradient / Hessian-vector product)
     void rowsum_users(const double *x, double *out, const uint8_t *active, int zero_if_empty) {
         k_rowsum(ctx, X.un_seg, X.un_start, nullptr, X.n_units, X.seg_unit_ptr, nullptr, d1, X.item, nullptr, cbuf, V, ld, active, partial,
-                 cfg.lambda, x, out, zero_if_empty, active ? 0.0 : pass_bytes(X.nnz, d1));
+                 cfg.lambda, x, out, zero_if_empty, active ? 0.0 : pass_bytes(X.nnz, d1), k);
     }
 
     void require_ready() {
@@ -680,7 +681,7 @@ struct Engine {
         DevCsr &C = which == 0 ? X : XT;
         PCR_REQUIRE(which == 0 || has_test, "no test set loaded");
         double *sc = which == 0 ? b : ev_score_t;
-        k_dots(ctx, U, C.user, V, C.item, C.nnz, ld, nullptr, sc, 0.0);
+        k_dots(ctx, U, C.user, V, C.item, C.nnz, ld, k, nullptr, sc, 0.0);
         k_eval_pairs(ctx, C, sc, ev_err_item);
         k_eval_users(ctx, C, sc, ev_err_item, cfg.ndcg_k, ev_a, ev_b, ev_c, ev_d);
         k_sum(ctx, ev_a, C.d1, red_partials, slots + 0);
@@ -1071,7 +1072,7 @@ int primalcr_predict(const double *U, int64_t d1, const double *V, int64_t d2, i
     PCR_CUDA(cudaMemcpyAsync(ud, user, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
     PCR_CUDA(cudaMemcpyAsync(id, item, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
     pcr::k_pad_copy(ctx, Uc, d1, k, ld, Ud); pcr::k_pad_copy(ctx, Vc, d2, k, ld, Vd);
-    pcr::k_dots(ctx, Ud, ud, Vd, id, n, ld, nullptr, od, 0.0);
+    pcr::k_dots(ctx, Ud, ud, Vd, id, n, ld, k, nullptr, od, 0.0);
     if (n) PCR_CUDA(cudaMemcpyAsync(out, od, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
     PCR_CUDA(cudaStreamSynchronize(st));
     cudaStreamDestroy(st);

@@ -129,10 +129,10 @@ __global__ void __launch_bounds__(256) dots_kernel(const double *__restrict__ P,
     }
 }
 
-void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const int32_t *qrow, i64 n, int ld,
+void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const int32_t *qrow, i64 n, int ld, int kk,
             const uint8_t *active, double *out, double bytes) {
     if (n <= 0) return;
-    const int nch = ld / 2;
+    const int nch = (kk + 1) / 2;      // 16-byte chunks that carry payload (rows are padded to ld for 128-byte alignment)
     if (nch <= 4) {
         LAUNCH(c, active ? "dots_active" : "dots", bytes, dots_kernel<4>, resident_grid(dots_kernel<4>, 256, 0, c.sms, (n + 63) / 64), 256, 0, P, prow, Q, qrow, n, nch, ld, active, out);
     } else {
@@ -205,9 +205,9 @@ static void launch_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start
 
 // returns false when no specialisation fits (caller falls back to k_dots)
 bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, const double *P, const double *Q,
-                  const int32_t *qrow, int ld, const uint8_t *active, double *out, double bytes) {
+                  const int32_t *qrow, int ld, int kk, const uint8_t *active, double *out, double bytes) {
     if (n_units <= 0) return true;
-    const int nch = ld / 2;
+    const int nch = (kk + 1) / 2;
 #define DU(G, NC) launch_dots_units<G, NC>(c, un_seg, un_start, n_units, P, Q, qrow, nch, ld, active, out, bytes); return true;
     if (nch <= 56) {
         switch ((nch + 7) / 8) { case 1: DU(8, 1) case 2: DU(8, 2) case 3: DU(8, 3) case 4: DU(8, 4) case 5: DU(8, 5) case 6: DU(8, 6) default: DU(8, 7) }
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) rowsum_finalize_kernel(const i64 *__restr
                                                               const double *__restrict__ partial, int ld,
                                                               const uint8_t *__restrict__ active, double lambda,
                                                               const double *__restrict__ x, double *__restrict__ out,
-                                                              int zero_if_empty) {
+                                                              int zero_if_empty, int kp /* payload columns, rest is padding */) {
     const int lane = threadIdx.x & 31;
     const i64 warp_global = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
     const i64 nwarps = ((i64)gridDim.x * 256) >> 5;
@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(256) rowsum_finalize_kernel(const i64 *__restr
         if (active && !active[seg]) continue;
         const i64 u0 = seg_unit_ptr[seg], u1 = seg_unit_ptr[seg + 1];
         for (int cidx = lane; cidx < ld; cidx += 32) {
+            if (cidx >= kp) { out[(size_t)seg * ld + cidx] = 0.0; continue; }      // keep the padding exactly zero
             double v = (x != nullptr && !(zero_if_empty && u0 == u1)) ? lambda * x[(size_t)seg * ld + cidx] : 0.0;
             i64 u = u0;
             for (; u + 4 <= u1; u += 4) {       // 4 independent loads in flight, summed in unit order
@@ -300,8 +301,8 @@ __global__ void __launch_bounds__(256) rowsum_finalize_kernel(const i64 *__restr
 void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_end, i64 n_units, const i64 *seg_unit_ptr,
               const int32_t *seg_unit_idx, i64 n_seg, const int32_t *ridx, const int32_t *widx, const double *w, const double *M, int ld,
               const uint8_t *active, double *partial, double lambda, const double *x, double *out,
-              int zero_if_empty, double bytes) {
-    const int nch = ld / 2;
+              int zero_if_empty, double bytes, int kk) {
+    const int nch = (kk + 1) / 2;
     const int NCH = (nch + 31) / 32;
     PCR_REQUIRE(NCH <= 4, "rank too large for rowsum kernel (k <= 256)");
     const char *rs_name = widx ? "rowsum_items" : (active ? "rowsum_users_active" : "rowsum_users");
@@ -323,7 +324,7 @@ void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_
     }
     if (n_seg > 0)
         LAUNCH(c, "rowsum_finalize", 0.0, rowsum_finalize_kernel, grid_for(n_seg, 8, c.sms * 8), 256, 0, seg_unit_ptr, seg_unit_idx, n_seg,
-               partial, ld, active, lambda, x, out, zero_if_empty);
+               partial, ld, active, lambda, x, out, zero_if_empty, 2 * nch);
 }
 
 // ------------------------------------------------------------------ K2: per-user bitonic sort (classes S and L)

@@ -26,17 +26,17 @@ void k_heavy_sort(Ctx &c, DevPool &pool, void **temp, size_t *temp_bytes, const 
 
 // ---------------------------------------------------------------- k_core.cu
 // out[e] = P[prow[e]] . Q[qrow[e]]  (rows are ld-strided, ld % 4 == 0); skipped when active[prow[e]] == 0
-void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const int32_t *qrow, i64 n, int ld,
+void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const int32_t *qrow, i64 n, int ld, int kk,
             const uint8_t *active, double *out, double bytes);
 // same as k_dots for the training set, user-major over row-sum units (P row in registers); false => use k_dots
 bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, const double *P, const double *Q,
-                  const int32_t *qrow, int ld, const uint8_t *active, double *out, double bytes);
+                  const int32_t *qrow, int ld, int kk, const uint8_t *active, double *out, double bytes);
 // out[seg] = lambda*x[seg] + sum_{e in seg} w[widx ? widx[e] : e] * M[ridx[e]]   (deterministic two-phase)
 // un_end == nullptr: unit u covers [un_start[u], un_start[u+1]); seg_unit_idx == nullptr: a segment's units are contiguous
 void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_end, i64 n_units, const i64 *seg_unit_ptr,
               const int32_t *seg_unit_idx, i64 n_seg, const int32_t *ridx, const int32_t *widx, const double *w, const double *M, int ld,
               const uint8_t *active, double *partial, double lambda, const double *x, double *out,
-              int zero_if_empty, double bytes);
+              int zero_if_empty, double bytes, int kk);
 // per-user sort of scores (classes S and L, bitonic in shared memory); writes s / pos / lev
 void k_sort_users(Ctx &c, int cls, const int32_t *users, int n_users, const uint8_t *active, const i64 *row_ptr,
                   const double *m, const uint8_t *level, SortedMeta &meta);
