@@ -12,6 +12,8 @@
 //   vec         K5  CG vector algebra of solve_delta_new :335-358
 #include "kernels.h"
 #include <math_constants.h>
+#include <algorithm>
+#include <cstdlib>
 
 namespace pcr {
 
@@ -247,6 +249,9 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const int32_t *__restrict__
             int ri = 0; double wi = 0.0;
             if (me < e) { ri = ridx[me]; wi = widx ? w[widx[me]] : w[me]; }
             const int cnt = (e - base) < 32 ? (int)(e - base) : 32;
+            // (measured: forcing 8 or 16 loads per lane in flight with an explicit load-then-FMA batch costs more in
+            //  occupancy than it gains -- 89 ms and 206 ms vs 73 ms per step for the item-major pass; the compiler's own
+            //  interleaving of this 4x unrolled loop at 56 registers is the fastest variant)
 #pragma unroll 4
             for (int j = 0; j < cnt; ++j) {
                 const int r = __shfl_sync(FULL, ri, j);
@@ -262,6 +267,129 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const int32_t *__restrict__
                     }
                 }
             }
+        }
+        double2 *o = reinterpret_cast<double2 *>(partial + (size_t)u * ld);
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) { const int ci = lane + 32 * q; if (ci < nch) o[ci] = acc[q]; }
+    }
+}
+
+// ------------------------------------------------------------------ K4 (bulk-async variant): rows staged by the TMA unit
+// EXPERIMENT, off by default (PRIMALCR_ROWSUM_TMA=1 enables it; parity-tested).  Every lane asks the TMA unit for one
+// whole row (cp.async.bulk, global -> shared memory, completion on an mbarrier), two stages per warp, and the FMAs read
+// the rows from shared memory.  Measured on B200 (Netflix-shape, k=100, 800-byte rows): 11.4 ms per item-major pass
+// against 6.6 ms for the register variant, i.e. about one 800-byte bulk copy per 33 cycles per SM -- the per-request cost
+// of cp.async.bulk is too high for rows this short.  Kept for longer rows (k >= 400) and as a record of the measurement.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+static const int TMA_WARPS = 8;                 // warps per CTA
+static const int TMA_WARP_BYTES = 25 * 1024;    // shared memory per warp (two stages)
+
+template <int NCH>
+__global__ void __launch_bounds__(TMA_WARPS * 32, 1) rowsum_tma_kernel(const int32_t *__restrict__ un_seg,
+                                                                        const i64 *__restrict__ un_start,
+                                                                        const i64 *__restrict__ un_end, i64 n_units,
+                                                                        unsigned long long *__restrict__ ticket,
+                                                                        const int32_t *__restrict__ ridx,
+                                                                        const int32_t *__restrict__ widx,
+                                                                        const double *__restrict__ w,
+                                                                        const double *__restrict__ M, int ld, int nch, int rs,
+                                                                        const uint8_t *__restrict__ active,
+                                                                        double *__restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    __shared__ __align__(8) uint64_t bars[TMA_WARPS][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t rb = (uint32_t)nch * 16u;                 // payload bytes of one row
+    unsigned char *stage0 = tma_smem + (size_t)warp * TMA_WARP_BYTES;
+    unsigned char *stage1 = stage0 + (size_t)rs * rb;
+    if (lane == 0) { mbar_init(&bars[warp][0], 1); mbar_init(&bars[warp][1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    uint32_t phase0 = 0, phase1 = 0;
+    for (;;) {
+        unsigned long long tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1ull);
+        const i64 u = (i64)__shfl_sync(FULL, tk, 0);
+        if (u >= n_units) break;
+        const int seg = un_seg[u];
+        if (active && !active[seg]) continue;
+        const i64 b = un_start[u], e = un_end ? un_end[u] : un_start[u + 1];
+        double2 acc[NCH];
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) acc[q] = make_double2(0.0, 0.0);
+        const i64 nb = (e - b + rs - 1) / rs;                 // batches of rs rows
+        // prologue: batch 0 -> stage 0
+        double wcur = 0.0, wnext = 0.0;
+        {
+            const i64 me = b + lane;
+            const bool on = lane < rs && me < e;
+            int ri = 0;
+            if (on) { ri = ridx[me]; wcur = widx ? w[widx[me]] : w[me]; }
+            const int cnt = (int)((e - b) < rs ? (e - b) : rs);
+            if (lane == 0) mbar_expect_tx(&bars[warp][0], (uint32_t)cnt * rb);
+            __syncwarp();
+            if (on) bulk_g2s(stage0 + (size_t)lane * rb, M + (size_t)ri * ld, rb, &bars[warp][0]);
+        }
+        for (i64 bi = 0; bi < nb; ++bi) {
+            const int cur = (int)(bi & 1);
+            // prefetch batch bi+1 into the other stage (its previous contents were consumed in iteration bi-1)
+            if (bi + 1 < nb) {
+                const i64 base = b + (bi + 1) * rs;
+                const i64 me = base + lane;
+                const bool on = lane < rs && me < e;
+                int ri = 0;
+                wnext = 0.0;
+                if (on) { ri = ridx[me]; wnext = widx ? w[widx[me]] : w[me]; }
+                const int cnt = (int)((e - base) < rs ? (e - base) : rs);
+                uint64_t *bar = &bars[warp][cur ^ 1];
+                if (lane == 0) mbar_expect_tx(bar, (uint32_t)cnt * rb);
+                __syncwarp();
+                if (on) bulk_g2s((cur ? stage0 : stage1) + (size_t)lane * rb, M + (size_t)ri * ld, rb, bar);
+            }
+            // consume batch bi
+            const i64 base = b + bi * rs;
+            const int cnt = (int)((e - base) < rs ? (e - base) : rs);
+            if (cur == 0) { mbar_wait(&bars[warp][0], phase0); phase0 ^= 1u; }
+            else          { mbar_wait(&bars[warp][1], phase1); phase1 ^= 1u; }
+            const unsigned char *st = cur ? stage1 : stage0;
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+                const double ww = __shfl_sync(FULL, wcur, j);
+                const double2 *row = reinterpret_cast<const double2 *>(st + (size_t)j * rb);
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) {
+                    const int ci = lane + 32 * q;
+                    if (ci < nch) {
+                        const double2 x = row[ci];
+                        acc[q].x = fma(ww, x.x, acc[q].x);
+                        acc[q].y = fma(ww, x.y, acc[q].y);
+                    }
+                }
+            }
+            wcur = wnext;
+            __syncwarp();        // every lane is done reading this stage before it is refilled
         }
         double2 *o = reinterpret_cast<double2 *>(partial + (size_t)u * ld);
 #pragma unroll
@@ -307,19 +435,23 @@ void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_
     PCR_REQUIRE(NCH <= 4, "rank too large for rowsum kernel (k <= 256)");
     const char *rs_name = widx ? "rowsum_items" : (active ? "rowsum_users_active" : "rowsum_users");
     if (n_units > 0) {
-        unsigned grid = 1;
-        switch (NCH) {
-            case 1: grid = resident_grid(rowsum_kernel<1>, 256, 0, c.sms, (n_units + 7) / 8); break;
-            case 2: grid = resident_grid(rowsum_kernel<2>, 256, 0, c.sms, (n_units + 7) / 8); break;
-            case 3: grid = resident_grid(rowsum_kernel<3>, 256, 0, c.sms, (n_units + 7) / 8); break;
-            default: grid = resident_grid(rowsum_kernel<4>, 256, 0, c.sms, (n_units + 7) / 8); break;
-        }
         PCR_CUDA(cudaMemsetAsync(c.ticket, 0, sizeof(unsigned long long), c.stream));
-        switch (NCH) {
-            case 1: LAUNCH(c, rs_name, bytes, rowsum_kernel<1>, grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); break;
-            case 2: LAUNCH(c, rs_name, bytes, rowsum_kernel<2>, grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); break;
-            case 3: LAUNCH(c, rs_name, bytes, rowsum_kernel<3>, grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); break;
-            default: LAUNCH(c, rs_name, bytes, rowsum_kernel<4>, grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); break;
+        static const bool use_tma = getenv("PRIMALCR_ROWSUM_TMA") != nullptr && atoi(getenv("PRIMALCR_ROWSUM_TMA")) != 0;
+        const int rb = nch * 16;
+        int rs = TMA_WARP_BYTES / 2 / rb;
+        if (rs > 32) rs = 32;
+        if (use_tma && rs >= 4) {
+            const size_t sm = (size_t)TMA_WARPS * TMA_WARP_BYTES;
+            const unsigned g = (unsigned)std::min<i64>((i64)c.sms, (n_units + TMA_WARPS - 1) / TMA_WARPS);
+#define RT(N) { PCR_CUDA(cudaFuncSetAttribute(rowsum_tma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+                LAUNCH(c, rs_name, bytes, rowsum_tma_kernel<N>, g, TMA_WARPS * 32, sm, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, rs, active, partial); }
+            switch (NCH) { case 1: RT(1) break; case 2: RT(2) break; case 3: RT(3) break; default: RT(4) break; }
+#undef RT
+        } else {
+#define RS(N) { const unsigned grid = resident_grid(rowsum_kernel<N>, 256, 0, c.sms, (n_units + 7) / 8); \
+                LAUNCH(c, rs_name, bytes, rowsum_kernel<N>, grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); }
+            switch (NCH) { case 1: RS(1) break; case 2: RS(2) break; case 3: RS(3) break; default: RS(4) break; }
+#undef RS
         }
     }
     if (n_seg > 0)
