@@ -152,6 +152,15 @@ struct Engine {
         C.item = upload(item, (size_t)nnz);
         C.rating = upload(rating, (size_t)nnz);
         C.user = pool.alloc<int32_t>((size_t)nnz);
+        {   // item ids are used as array indices by every kernel: validate them first
+            int *bad = pool.alloc<int>(1);
+            PCR_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), stream));
+            k_check_range(ctx, C.item, nnz, d2, bad);
+            PCR_CUDA(cudaMemcpyAsync(h_counters, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            PCR_CUDA(cudaStreamSynchronize(stream));
+            PCR_REQUIRE(h_counters[0] == 0, "item id out of range [0, d2)");
+        }
+        for (i64 u = 0; u < d1_; ++u) PCR_REQUIRE(C.h_row_ptr[u + 1] >= C.h_row_ptr[u], "row_ptr must be non-decreasing");
         k_expand_users(ctx, C.row_ptr, d1_, nnz, C.user);
         // pair-tile work items
         std::vector<int32_t> ptu, ptj; std::vector<i64> ptp((size_t)d1_ + 1, 0);
@@ -188,12 +197,24 @@ struct Engine {
         levels_user_set = true;
     }
 
+    struct Lap {
+        bool on; std::chrono::steady_clock::time_point t;
+        Lap() : on(getenv("PRIMALCR_VERBOSE_SETUP") != nullptr), t(std::chrono::steady_clock::now()) {}
+        void operator()(const char *what) {
+            if (!on) return;
+            auto n = std::chrono::steady_clock::now();
+            fprintf(stderr, "[primalcr setup] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+            t = n;
+        }
+    };
     void set_train(i64 d1_, i64 d2_, i64 nnz, const i64 *row_ptr, const int32_t *item, const double *rating) {
         bind();
+        Lap lap;
         PCR_REQUIRE(!has_train, "training set already loaded (one data set per engine)");
         PCR_REQUIRE(d1_ >= 0 && d2_ >= 1 && nnz >= 0, "bad sizes");
         d1 = d1_; d2 = d2_;
         build_csr_common(X, d1_, nnz, row_ptr, item, rating);
+        lap("upload CSR + pair tiles");
         // ---- rating levels (find_levels pcrpp.cpp:38-49, as one global order-preserving table)
         if (!levels_user_set) {
             i64 lo = 0, hi = 0; bool any = false;
@@ -227,6 +248,7 @@ struct Engine {
         PCR_CUDA(cudaMemcpyAsync(h_counters, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
         sync();
         PCR_REQUIRE(h_counters[0] == 0, "a rating rounds to a level that is not in the level table");
+        lap("levels");
         // ---- size classes, heavy scratch
         std::vector<int32_t> cls[3];
         std::vector<i64> hoff((size_t)d1, -1), hb, he;
@@ -274,6 +296,7 @@ struct Engine {
         X.n_units = (i64)useg.size();
         X.un_seg = upload_vec(useg); X.un_start = upload_vec(ustart); X.seg_unit_ptr = upload_vec(supt);
         sync();
+        lap("classes, tiles, user units");
         // ---- CSC by item + its work units
         col_ptr = pool.alloc<i64>((size_t)d2 + 1);
         csc2csr = pool.alloc<int32_t>((size_t)nnz); csc_user = pool.alloc<int32_t>((size_t)nnz);
@@ -282,6 +305,7 @@ struct Engine {
         PCR_CUDA(cudaMemcpyAsync(h_col.data(), col_ptr, sizeof(i64) * ((size_t)d2 + 1), cudaMemcpyDeviceToHost, stream));
         sync();
         PCR_REQUIRE(h_col[d2] == nnz, "item id out of range [0, d2)");
+        lap("CSC build (device)");
         // Work units of the item-major row sum, ordered USER-BLOCK-major: every unit only touches U rows of one block
         // of <= ~40 MB, so while the persistent grid walks the unit list the gathered rows stay L2-resident
         // (users ascend inside a column, so a column's entries of one block are contiguous).
@@ -321,6 +345,7 @@ struct Engine {
             col_unit_ptr = upload_vec(csup); col_unit_idx = upload_vec(cidx);
             sync();
         }
+        lap("item units (user blocks)");
         // ---- work buffers
         m = pool.alloc<double>((size_t)nnz); b = pool.alloc<double>((size_t)nnz); cbuf = pool.alloc<double>((size_t)nnz);
         meta.s = pool.alloc<double>((size_t)nnz); meta.pos = pool.alloc<int32_t>((size_t)nnz);
@@ -357,6 +382,7 @@ struct Engine {
         obj_item = pool.alloc<double>((size_t)X.n_pt);
         ensure_eval_buffers(X);
         sync();
+        lap("work buffers");
         has_train = true;
     }
 

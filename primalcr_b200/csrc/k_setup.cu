@@ -59,6 +59,18 @@ void k_iota32(Ctx &c, int32_t *out, i64 n) {
     LAUNCH(c, "iota32", 0.0, iota32_kernel, grid_for(n, 256, c.sms * 16), 256, 0, out, n);
 }
 
+// number of entries whose id lies outside [0, bound): checked BEFORE any kernel indexes with them
+__global__ void count_out_of_range_kernel(const int32_t *__restrict__ idx, i64 n, i64 bound, int *__restrict__ bad) {
+    int local = 0;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (i64)gridDim.x * blockDim.x)
+        if (idx[e] < 0 || (i64)idx[e] >= bound) local = 1;
+    if (local) atomicOr(bad, 1);
+}
+void k_check_range(Ctx &c, const int32_t *idx, i64 n, i64 bound, int *bad_flag) {
+    if (n <= 0) return;
+    LAUNCH(c, "check_range", 0.0, count_out_of_range_kernel, grid_for(n, 256, c.sms * 16), 256, 0, idx, n, bound, bad_flag);
+}
+
 __global__ void hist_kernel(const int32_t *__restrict__ item, i64 nnz, unsigned long long *__restrict__ counts) {
     for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (i64)gridDim.x * blockDim.x)
         atomicAdd(&counts[item[e]], 1ull);

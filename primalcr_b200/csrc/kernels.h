@@ -15,6 +15,7 @@ struct Ctx {               // what every launcher needs
 void k_expand_users(Ctx &c, const i64 *row_ptr, i64 d1, i64 nnz, int32_t *user_out);
 void k_levels(Ctx &c, const double *rating, i64 nnz, const i64 *table_dev, int T, uint8_t *level_out, int *bad_flag);
 void k_iota32(Ctx &c, int32_t *out, i64 n);
+void k_check_range(Ctx &c, const int32_t *idx, i64 n, i64 bound, int *bad_flag);   // *bad_flag |= 1 if any idx outside [0, bound)
 // bpos[p*(nb+1)+j] = first CSC position of column p whose user id is >= j*block_users (users ascend inside a column)
 void k_csc_block_bounds(Ctx &c, const i64 *col_ptr, const int32_t *csc_user, i64 d2, int nb, i64 block_users, i64 *bpos);
 // CSC (by item) of a CSR: col_ptr[d2+1], csc2csr[nnz] (stable: users ascending inside an item), csc_user[nnz]

@@ -372,3 +372,74 @@ def test_own_cli_train_and_predict(tmp_path, solver):
     assert out2.returncode == 0, out2.stderr
     o = [float(l.split()[-1]) for l in out2.stdout.splitlines() if l.startswith("Iter ")]
     assert abs(o[0] - float(g["s%d_obj" % solver][iters])) <= 2e-5 * o[0] and o[1] < o[0]
+
+
+def _custom_dataset(lens, d2, levels, seed):
+    from primalcr_b200.data import Dataset, Ratings
+    rng = np.random.default_rng(seed)
+    users, items, vals = [], [], []
+    for u, n in enumerate(lens):
+        users.append(np.full(n, u)); items.append(np.sort(rng.choice(d2, size=n, replace=False)))
+        vals.append(rng.integers(1, levels + 1, size=n).astype(np.float64))
+    d1 = len(lens)
+    tr = Ratings.from_coo(d1, d2, np.concatenate(users), np.concatenate(items), np.concatenate(vals)) if sum(lens) else Ratings.empty(d1, d2)
+    return Dataset(tr, Ratings.empty(d1, d2))
+
+
+@pytest.mark.parametrize("levels,k", [(7, 9), (2, 4), (8, 3), (12, 5)])
+def test_level_count_variants(levels, k):
+    """2, 7 and 8 rating levels go through the tile kernels (5- and 8-level instantiations), 12 levels through the
+    per-user kernels: one outer iteration against the oracle for each."""
+    ds = _custom_dataset([0, 3, 40, 1, 700, 129, 1500, 64, 2, 31], 2000, levels, seed=levels)
+    lam = 15.0
+    e, U, V = make_engine(ds, k, lam, test=False)
+    res = ob.oracle().train(2, to_csr(ds.train), None, U, V, lam, 2, do_predict=0)
+    assert abs(e.initial_objective() - res["obj"][0]) <= OBJ_TOL * res["obj"][0]
+    for i in (1, 2):
+        o = e.outer_iteration()
+        assert abs(o - res["obj"][i]) <= OBJ_TOL * res["obj"][i], (levels, i)
+        c = e.counters(); cnt = res["counters"][i - 1]
+        assert (c["v_cg_iters"], c["v_ls_trials"], c["u_cg_len_sum"], c["u_ls_len_sum"], c["u_skipped"]) == \
+            (cnt[0], cnt[1], cnt[3], cnt[4], cnt[5])
+    Ug, Vg = e.get_factors()
+    assert rel(Ug, res["U"]) < 1e-7 and rel(Vg, res["V"]) < 1e-7
+    e.close()
+
+
+@pytest.mark.parametrize("solver", [2, 1])
+def test_empty_and_degenerate_inputs(solver):
+    """No ratings at all, a single rating, a single user: the reference's loops simply do not execute; U and V only
+    feel the regulariser.  Must not crash, hang or produce NaN, and must agree with the oracle."""
+    from primalcr_b200.data import Dataset, Ratings
+    for lens in ([0, 0, 0], [0, 1, 0], [5]):
+        ds = _custom_dataset(lens, 6, 3, seed=1)
+        k, lam = 3, 2.0
+        U, V = np_init(ds.d1, ds.d2, k, seed=1)
+        e, _, _ = make_engine(ds, k, lam, solver=solver, U=U, V=V, test=False, levels=False)
+        res = ob.oracle().train(solver, to_csr(ds.train) if ds.train.nnz else ob.Csr.empty(ds.d1, ds.d2), None, U, V, lam, 1, do_predict=0)
+        o0 = e.initial_objective(); o1 = e.outer_iteration()
+        assert np.isfinite(o0) and np.isfinite(o1)
+        assert abs(o0 - res["obj"][0]) <= 1e-12 * max(res["obj"][0], 1.0)
+        assert abs(o1 - res["obj"][1]) <= 1e-9 * max(res["obj"][1], 1.0)
+        Ug, Vg = e.get_factors()
+        assert np.abs(Ug - res["U"]).max() < 1e-9 and np.abs(Vg - res["V"]).max() < 1e-9
+        e.close()
+
+
+def test_bad_inputs_are_rejected():
+    from primalcr_b200.data import Ratings
+    p = api.Parameter(k=4)
+    e = api.Engine(p)
+    bad = Ratings(2, 5, np.array([0, 1, 2], np.int64), np.array([1, 7], np.int32), np.array([1.0, 2.0]))
+    with pytest.raises(api.PrimalCRError, match="out of range"):
+        e.set_train(bad)
+    e.close()
+    e = api.Engine(p)
+    with pytest.raises(api.PrimalCRError):
+        e.initial_objective()                 # nothing loaded yet
+    many = Ratings(1, 50, np.array([0, 40], np.int64), np.arange(40, dtype=np.int32), np.arange(40, dtype=np.float64))
+    with pytest.raises(api.PrimalCRError, match="32"):
+        e.set_train(many)                     # more than 32 distinct rating levels
+    e.close()
+    with pytest.raises(api.PrimalCRError):
+        api.Engine(api.Parameter(k=0))
