@@ -120,7 +120,9 @@ struct DevCsr {
     i64 *pt_ptr = nullptr;       // [d1+1] first work item of each user
     // row-sum work units over this CSR (segments = users)
     int32_t *un_seg = nullptr; i64 *un_start = nullptr; i64 n_units = 0;   // un_start[n_units+1]
+    i64 *un_end = nullptr;       // only when the units are item-block ordered (then un_start is not contiguous)
     i64 *seg_unit_ptr = nullptr; // [d1+1]
+    int32_t *seg_unit_idx = nullptr;   // unit ids grouped by user (item-block order), else nullptr
 };
 
 struct SortedMeta {          // per rating, in (user, ascending score) order

@@ -67,7 +67,7 @@ struct Engine {
     // CSC of the training set (by item)
     i64 *col_ptr = nullptr; int32_t *csc_user = nullptr, *csc2csr = nullptr;
     int32_t *cu_seg = nullptr; i64 *cu_start = nullptr, *cu_end = nullptr; i64 n_cunits = 0; i64 *col_unit_ptr = nullptr;
-    int32_t *col_unit_idx = nullptr; int n_user_blocks = 1;
+    int32_t *col_unit_idx = nullptr; int n_user_blocks = 1, n_item_blocks = 1;
     // factors (padded leading dimension ld)
     double *U = nullptr, *V = nullptr;
     // per-rating work buffers
@@ -291,11 +291,52 @@ struct Engine {
         h_p2 = pool.alloc<double>((size_t)htot); h_acc = pool.alloc<double>((size_t)htot);
         h_cnt = pool.alloc<int32_t>((size_t)htot);
         // ---- row-sum work units over the CSR
-        std::vector<int32_t> useg; std::vector<i64> ustart, supt;
-        make_units(X.h_row_ptr, useg, ustart, supt);
-        X.n_units = (i64)useg.size();
-        X.un_seg = upload_vec(useg); X.un_start = upload_vec(ustart); X.seg_unit_ptr = upload_vec(supt);
-        sync();
+        const double blk_bytes = getenv("PRIMALCR_UBLOCK_MB") ? atof(getenv("PRIMALCR_UBLOCK_MB")) * 1e6 : 24e6;
+        const double v_bytes = (double)d2 * ld * 8.0;
+        if (v_bytes > 4.0 * blk_bytes && getenv("PRIMALCR_ITEM_BLOCKS") != nullptr) {
+            // OPT-IN EXPERIMENT (PRIMALCR_ITEM_BLOCKS=1): when V does not fit L2 (Yahoo shape, 500 MB) order the
+            // user-major units ITEM-BLOCK-major so that the V rows gathered by dots / the user-major row sum come from one
+            // <= 24 MB block at a time (items ascend inside a user, so a user's entries of one block are contiguous) --
+            // the mirror image of the CSC user blocks below.  Measured on the full Yahoo shape: 1.26 s vs 1.14 s per
+            // iteration WITHOUT it: 21 blocks x 1 M users give 21 M units of ~12 ratings, and re-fetching the user's row
+            // per unit costs more than the L2 hits save.  Off by default; parity-tested.
+            int nb = (int)std::ceil(v_bytes / blk_bytes);
+            if (nb > 64) nb = 64;
+            const i64 bi = (d2 + nb - 1) / nb;
+            n_item_blocks = nb;
+            std::vector<i64> bpos((size_t)d1 * (nb + 1));
+            i64 *bpos_d = nullptr;
+            PCR_CUDA(cudaMalloc(&bpos_d, sizeof(i64) * std::max<size_t>(bpos.size(), 1)));
+            k_csc_block_bounds(ctx, X.row_ptr, X.item, d1, nb, bi, bpos_d);
+            PCR_CUDA(cudaMemcpyAsync(bpos.data(), bpos_d, sizeof(i64) * bpos.size(), cudaMemcpyDeviceToHost, stream));
+            sync();
+            cudaFree(bpos_d);
+            std::vector<int32_t> useg, uidx; std::vector<i64> ustart, uend, supt((size_t)d1 + 1, 0);
+            useg.reserve((size_t)d1 * 4); ustart.reserve((size_t)d1 * 4); uend.reserve((size_t)d1 * 4);
+            for (int blk = 0; blk < nb; ++blk)
+                for (i64 u = 0; u < d1; ++u) {
+                    const i64 lo = bpos[(size_t)u * (nb + 1) + blk];
+                    const i64 hi = blk + 1 == nb ? X.h_row_ptr[u + 1] : bpos[(size_t)u * (nb + 1) + blk + 1];
+                    for (i64 bb = lo; bb < hi; bb += ROWSUM_CHUNK) {
+                        useg.push_back((int32_t)u); ustart.push_back(bb); uend.push_back(std::min<i64>(bb + ROWSUM_CHUNK, hi));
+                        supt[u + 1] += 1;
+                    }
+                }
+            X.n_units = (i64)useg.size();
+            for (i64 u = 0; u < d1; ++u) supt[u + 1] += supt[u];
+            uidx.resize(useg.size());
+            std::vector<i64> fill(supt.begin(), supt.end() - 1);
+            for (size_t q = 0; q < useg.size(); ++q) uidx[fill[useg[q]]++] = (int32_t)q;
+            X.un_seg = upload_vec(useg); X.un_start = upload_vec(ustart); X.un_end = upload_vec(uend);
+            X.seg_unit_ptr = upload_vec(supt); X.seg_unit_idx = upload_vec(uidx);
+            sync();
+        } else {
+            std::vector<int32_t> useg; std::vector<i64> ustart, supt;
+            make_units(X.h_row_ptr, useg, ustart, supt);
+            X.n_units = (i64)useg.size();
+            X.un_seg = upload_vec(useg); X.un_start = upload_vec(ustart); X.seg_unit_ptr = upload_vec(supt);
+            sync();
+        }
         lap("classes, tiles, user units");
         // ---- CSC by item + its work units
         col_ptr = pool.alloc<i64>((size_t)d2 + 1);
@@ -311,7 +352,6 @@ struct Engine {
         // (users ascend inside a column, so a column's entries of one block are contiguous).
         {
             const double u_bytes = (double)d1 * ld * 8.0;
-            const double blk_bytes = getenv("PRIMALCR_UBLOCK_MB") ? atof(getenv("PRIMALCR_UBLOCK_MB")) * 1e6 : 24e6;
             int nb = (int)std::ceil(u_bytes / blk_bytes);
             if (nb < 1) nb = 1;
             if (nb > 64) nb = 64;
@@ -474,7 +514,7 @@ struct Engine {
     // out[e] = P[user(e)] . Q[item(e)] over the training set
     void train_dots(const double *P, const double *Q, double *out, const uint8_t *active) {
         const double bytes = active ? 0.0 : pass_bytes(X.nnz, d1);
-        if (!k_dots_units(ctx, X.un_seg, X.un_start, X.n_units, P, Q, X.item, ld, k, active, out, bytes))
+        if (!k_dots_units(ctx, X.un_seg, X.un_start, X.un_end, X.n_units, P, Q, X.item, ld, k, active, out, bytes))
             k_dots(ctx, P, X.user, Q, X.item, X.nnz, ld, k, active, out, bytes);
     }
     // get_sorted_mm + window pointers for every (active) user
@@ -535,7 +575,7 @@ struct Engine {
     }
     // out[i] = lambda*x[i] + sum over user i of cbuf[e] * V[item(e)]   (U-side gradient / Hessian-vector product)
     void rowsum_users(const double *x, double *out, const uint8_t *active, int zero_if_empty) {
-        k_rowsum(ctx, X.un_seg, X.un_start, nullptr, X.n_units, X.seg_unit_ptr, nullptr, d1, X.item, nullptr, cbuf, V, ld, active, partial,
+        k_rowsum(ctx, X.un_seg, X.un_start, X.un_end, X.n_units, X.seg_unit_ptr, X.seg_unit_idx, d1, X.item, nullptr, cbuf, V, ld, active, partial,
                  cfg.lambda, x, out, zero_if_empty, active ? 0.0 : pass_bytes(X.nnz, d1), k);
     }
 

@@ -147,6 +147,7 @@ void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const
 // a rating's Q row are issued back to back before the first FMA (NC is a template parameter => fully unrolled).
 template <int G, int NC>
 __global__ void __launch_bounds__(256, 3) dots_units_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
+                                                         const i64 *__restrict__ un_end,
                                                          i64 n_units, unsigned long long *__restrict__ ticket,
                                                          const double *__restrict__ P,
                                                          const double *__restrict__ Q, const int32_t *__restrict__ qrow,
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(256, 3) dots_units_kernel(const int32_t *__res
         if (u >= n_units) break;
         const int seg = un_seg[u];
         if (active && !active[seg]) continue;           // warp-uniform
-        const i64 b = un_start[u], e = un_start[u + 1];
+        const i64 b = un_start[u], e = un_end ? un_end[u] : un_start[u + 1];
         double2 pr[NC];
         const double2 *p2 = reinterpret_cast<const double2 *>(P + (size_t)seg * ld);
 #pragma unroll
@@ -197,20 +198,20 @@ __global__ void __launch_bounds__(256, 3) dots_units_kernel(const int32_t *__res
 }
 
 template <int G, int NC>
-static void launch_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, const double *P, const double *Q,
+static void launch_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_end, i64 n_units, const double *P, const double *Q,
                               const int32_t *qrow, int nch, int ld, const uint8_t *active, double *out, double bytes) {
     const unsigned grid = resident_grid(dots_units_kernel<G, NC>, 256, 0, c.sms, (n_units + 7) / 8);
     PCR_CUDA(cudaMemsetAsync(c.ticket, 0, sizeof(unsigned long long), c.stream));
-    LAUNCH(c, active ? "dots_active" : "dots", bytes, (dots_units_kernel<G, NC>), grid, 256, 0, un_seg, un_start, n_units, c.ticket, P, Q, qrow,
+    LAUNCH(c, active ? "dots_active" : "dots", bytes, (dots_units_kernel<G, NC>), grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, P, Q, qrow,
            nch, ld, active, out);
 }
 
 // returns false when no specialisation fits (caller falls back to k_dots)
-bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, const double *P, const double *Q,
+bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_end, i64 n_units, const double *P, const double *Q,
                   const int32_t *qrow, int ld, int kk, const uint8_t *active, double *out, double bytes) {
     if (n_units <= 0) return true;
     const int nch = (kk + 1) / 2;
-#define DU(G, NC) launch_dots_units<G, NC>(c, un_seg, un_start, n_units, P, Q, qrow, nch, ld, active, out, bytes); return true;
+#define DU(G, NC) launch_dots_units<G, NC>(c, un_seg, un_start, un_end, n_units, P, Q, qrow, nch, ld, active, out, bytes); return true;
     if (nch <= 56) {
         switch ((nch + 7) / 8) { case 1: DU(8, 1) case 2: DU(8, 2) case 3: DU(8, 3) case 4: DU(8, 4) case 5: DU(8, 5) case 6: DU(8, 6) default: DU(8, 7) }
     } else if (nch <= 112) {

@@ -30,7 +30,7 @@ void k_heavy_sort(Ctx &c, DevPool &pool, void **temp, size_t *temp_bytes, const 
 void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const int32_t *qrow, i64 n, int ld, int kk,
             const uint8_t *active, double *out, double bytes);
 // same as k_dots for the training set, user-major over row-sum units (P row in registers); false => use k_dots
-bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, i64 n_units, const double *P, const double *Q,
+bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_end, i64 n_units, const double *P, const double *Q,
                   const int32_t *qrow, int ld, int kk, const uint8_t *active, double *out, double bytes);
 // out[seg] = lambda*x[seg] + sum_{e in seg} w[widx ? widx[e] : e] * M[ridx[e]]   (deterministic two-phase)
 // un_end == nullptr: unit u covers [un_start[u], un_start[u+1]); seg_unit_idx == nullptr: a segment's units are contiguous

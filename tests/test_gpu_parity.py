@@ -443,3 +443,30 @@ def test_bad_inputs_are_rejected():
     e.close()
     with pytest.raises(api.PrimalCRError):
         api.Engine(api.Parameter(k=0))
+
+
+@pytest.mark.parametrize("name,k", [("tiny", 7), ("ragged", 10)])
+def test_l2_block_ordered_work_lists(name, k, monkeypatch):
+    """With a (artificially tiny) L2 block size both work lists switch to their blocked order -- CSC units user-block-major,
+    user units item-block-major (the Yahoo / power-law shapes take this path at full size): results must not change."""
+    monkeypatch.setenv("PRIMALCR_UBLOCK_MB", "0.002")
+    monkeypatch.setenv("PRIMALCR_ITEM_BLOCKS", "1")
+    ds = dataset(name)
+    lam = 25.0
+    e, U, V = make_engine(ds, k, lam, test=False)
+    res = ob.oracle().train(2, to_csr(ds.train), None, U, V, lam, 2, do_predict=0)
+    assert abs(e.initial_objective() - res["obj"][0]) <= OBJ_TOL * res["obj"][0]
+    O = ob.oracle(); X = to_csr(ds.train)
+    m = O.comp_m(X, U, V)
+    assert rel(e.grad_V(), O.obtain_g_new(X, U, V, m, lam)) < VEC_TOL
+    g, _ = e.grad_U()
+    for u in range(0, ds.d1, max(1, ds.d1 // 10)):
+        a, b = int(ds.train.row_ptr[u]), int(ds.train.row_ptr[u + 1])
+        go, _, _ = O.user_stage(X.rows[a:b], X.vals[a:b], m[a:b], V, lam, U[u], U[u])
+        assert rel(g[u], go) < VEC_TOL or np.abs(go).max() == 0
+    for i in (1, 2):
+        o = e.outer_iteration()
+        assert abs(o - res["obj"][i]) <= OBJ_TOL * res["obj"][i]
+    Ug, Vg = e.get_factors()
+    assert rel(Ug, res["U"]) < 1e-7 and rel(Vg, res["V"]) < 1e-7
+    e.close()
