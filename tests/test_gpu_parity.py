@@ -174,7 +174,8 @@ def test_update_V_then_U(name, k, lam, solver):
 
 
 @pytest.mark.parametrize("solver", [2, 1])
-@pytest.mark.parametrize("name,k,lam,iters", [("tiny", 7, 50.0, 4), ("ragged", 10, 20.0, 3), ("ml1m", 10, 5000.0, 2)])
+@pytest.mark.parametrize("name,k,lam,iters", [("tiny", 7, 50.0, 4), ("ragged", 10, 20.0, 3), ("ml1m", 10, 5000.0, 2),
+                                              ("ml1m", 100, 5000.0, 1)])
 def test_training_trajectory(name, k, lam, iters, solver):
     """The pcrpp()/pcr() driver: objective per outer iteration, pairwise error and NDCG@10 vs the oracle."""
     if name == "ml1m" and solver == 1:
