@@ -236,12 +236,17 @@ def main_ours(args):
         dist.broadcast(buf, 0)
         return bytes(buf.cpu().numpy().tobytes())
 
+    comm_ready = [False]
+
     def new_engine(maxiter):
         p = api.Parameter(solver_type=api.PCRPP, k=k, lambda_=lam, maxiter=maxiter, do_predict=0, device=local)
         e = api.Engine(p)
         e.set_levels(levels)
         if world > 1:
-            e.comm_init(rank, world, fresh_uid())
+            # the NCCL communicator is per-process state (created once, cached by the library): later solver calls of
+            # the same process re-attach to it, exactly as a long-lived host application would
+            e.comm_init(rank, world, None if comm_ready[0] else fresh_uid())
+            comm_ready[0] = True
         return e
 
     def barrier():

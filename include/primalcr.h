@@ -87,6 +87,9 @@ int primalcr_get_factors(primalcr_engine *e, double *U, double *V);
 
 /* ---- multi-GPU: user shards + NCCL allreduce of the d2 x k V-side sums ------------------------- */
 int primalcr_nccl_unique_id(void *id128);                         /* 128-byte ncclUniqueId, made on rank 0 */
+/* id128 != NULL: create this (device, rank, world)'s communicator (collective: every rank calls it with the same id).
+   id128 == NULL : re-attach to the communicator this PROCESS created earlier for the same (device, rank, world);
+                   communicators are cached per process, so repeated solver calls pay ncclCommInitRank once. */
 int primalcr_comm_init(primalcr_engine *e, int rank, int world, const void *id128);
 
 /* ---- the solver: body of pcrpp() pcrpp.cpp:841-901 / pcr() pcr.cpp:616-704 ---------------------- */

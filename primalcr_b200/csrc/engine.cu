@@ -16,6 +16,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <random>
+#include <mutex>
 
 // ---- NCCL, bound at run time (only needed when world > 1) -----------------------------------------
 typedef struct { char internal[128]; } pcr_ncclUniqueId;
@@ -45,6 +46,14 @@ struct NcclApi {
     }
 };
 static NcclApi g_nccl;
+
+// Communicators are per-process state: the first engine of a (device, rank, world) creates one from a ncclUniqueId,
+// later engines of the same process may re-attach to it (primalcr_comm_init with a NULL id) instead of paying
+// ncclCommInitRank (~1-2 s) again.  Cached communicators live until the process exits.
+struct CommKey { int device, rank, world; bool operator<(const CommKey &o) const {
+    return device != o.device ? device < o.device : (rank != o.rank ? rank < o.rank : world < o.world); } };
+static std::map<CommKey, pcr_ncclComm_t> g_comm_cache;
+static std::mutex g_comm_mutex;
 
 static thread_local std::string g_last_error;
 
@@ -122,8 +131,7 @@ struct Engine {
         stats_dev = pool.alloc<i64>(8);
     }
     ~Engine() {
-        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
-        cudaSetDevice(cfg.device);
+        cudaSetDevice(cfg.device);      // the communicator stays in the process-wide cache
         if (stream) cudaStreamSynchronize(stream);
         prof.resolve();
         pool.release();
@@ -887,12 +895,21 @@ int primalcr_comm_init(primalcr_engine *e, int rank, int world, const void *id12
     E->bind();
     E->rank = rank; E->world = world;
     if (world > 1) {
-        PCR_REQUIRE(id128 != nullptr, "null unique id");
-        if (!pcr::g_nccl.load()) throw pcr::Error(PRIMALCR_ENCCL, "cannot load libnccl.so.2");
-        pcr_ncclUniqueId id; memcpy(&id, id128, sizeof(id));
-        int r = pcr::g_nccl.CommInitRank(&E->comm, world, id, rank);
-        if (r != 0) throw pcr::Error(PRIMALCR_ENCCL, std::string("ncclCommInitRank failed: ") +
-                                     (pcr::g_nccl.GetErrorString ? pcr::g_nccl.GetErrorString(r) : "?"));
+        const pcr::CommKey key{E->cfg.device, rank, world};
+        if (id128 == nullptr) {          // re-attach to this process's communicator
+            std::lock_guard<std::mutex> lock(pcr::g_comm_mutex);
+            auto it = pcr::g_comm_cache.find(key);
+            PCR_REQUIRE(it != pcr::g_comm_cache.end(), "no cached communicator for this (device, rank, world): pass a ncclUniqueId");
+            E->comm = it->second;
+        } else {
+            if (!pcr::g_nccl.load()) throw pcr::Error(PRIMALCR_ENCCL, "cannot load libnccl.so.2");
+            pcr_ncclUniqueId id; memcpy(&id, id128, sizeof(id));
+            int r = pcr::g_nccl.CommInitRank(&E->comm, world, id, rank);
+            if (r != 0) throw pcr::Error(PRIMALCR_ENCCL, std::string("ncclCommInitRank failed: ") +
+                                         (pcr::g_nccl.GetErrorString ? pcr::g_nccl.GetErrorString(r) : "?"));
+            std::lock_guard<std::mutex> lock(pcr::g_comm_mutex);
+            pcr::g_comm_cache[key] = E->comm;
+        }
     }
     API_END
 }
