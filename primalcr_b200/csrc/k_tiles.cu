@@ -164,12 +164,14 @@ __global__ void __launch_bounds__(TH) tile_prepare_kernel(const int32_t *__restr
     __shared__ TileShared<CAP> ts;
     __shared__ int wagg[TH / 32 * TT];
     __shared__ int wflag[TH / 32];
-    // dynamic layout: keys[CAP] f64 | C[T][SLOTS] i32 | tag[CAP] u32 | lev[CAP] u8 | lev0[CAP] u8
+    // dynamic layout: keys[CAP] f64 | pk[CAP] u64 | C[T][SLOTS] i32 | tag[CAP] u32 | lev[CAP] u8 | lev0[CAP] u8
     double *keys = reinterpret_cast<double *>(smraw);
-    int *C = reinterpret_cast<int *>(keys + CAP);
+    unsigned long long *pk = reinterpret_cast<unsigned long long *>(keys + CAP);
+    int *C = reinterpret_cast<int *>(pk + CAP);
     uint32_t *tag = reinterpret_cast<uint32_t *>(C + T * SLOTS);
     uint8_t *slev = reinterpret_cast<uint8_t *>(tag + CAP);
     uint8_t *lev0 = slev + CAP;
+    __shared__ int s_fallback;
     const int tid = threadIdx.x;
     const int first_user = tile_first[blockIdx.x], n_users = tile_nusers[blockIdx.x];
     const i64 e0 = tile_e0[blockIdx.x];
@@ -190,29 +192,99 @@ __global__ void __launch_bounds__(TH) tile_prepare_kernel(const int32_t *__restr
         if (i < ne) { r_m[q] = m[e0 + i]; r_u[q] = user_of[e0 + i] - first_user; r_l[q] = level[e0 + i]; }
     }
     if (!users_done) tile_users<TH>(ts, first_user, n_users, e0, row_ptr, active);
+    // ---- sort, fast path: ONE 64-bit integer per rating, [user:7 | order-preserving float32 image of the score:32 |
+    // index:13], so a compare-exchange is a single 64-bit comparison; float32 rounding is monotone, hence the result can
+    // differ from the exact (user, fp64 score, index) order only inside runs of equal float images, which the odd-even
+    // fix-up below repairs with exact fp64 comparisons (zero or one sweep in practice).  keys[] keeps the fp64 scores in
+    // input order for that purpose.  If the fix-up does not settle (pathological clusters) the exact network is used.
 #pragma unroll
     for (int q = 0; q < TE; ++q) {
         const int i = tid + q * TH;
         if (i < np2) {
             keys[i] = r_m[q];
-            tag[i] = i < ne ? (((uint32_t)r_u[q] << 16) | (uint32_t)i) : 0xFFFFFFFFu;   // (user, index): padding last
-            if (i < ne) { ts.ul[i] = (uint8_t)r_u[q]; lev0[i] = r_l[q]; }
+            if (i < ne) {
+                const float f = (float)r_m[q] + 0.0f;                       // -0.0f -> +0.0f
+                const uint32_t b = __float_as_uint(f);
+                const uint32_t fk = b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+                pk[i] = ((unsigned long long)r_u[q] << 45) | ((unsigned long long)fk << 13) | (unsigned long long)i;
+                ts.ul[i] = (uint8_t)r_u[q]; lev0[i] = r_l[q];
+            } else {
+                pk[i] = ~0ull;
+            }
         }
     }
+    if (tid == 0) s_fallback = 0;
     __syncthreads();
-    // bitonic sort on the composite key (user, score, index)
     for (int k = 2; k <= np2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < (np2 >> 1); t += TH) {
                 const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const int p = i | j;
-                const bool asc = (i & k) == 0;
-                const uint32_t ti = tag[i], tp = tag[p];
-                const double ki = keys[i], kp = keys[p];
-                const bool gt = ((ti >> 16) != (tp >> 16)) ? (ti > tp) : ((ki > kp) || (ki == kp && ti > tp));
-                if (gt == asc) { keys[i] = kp; keys[p] = ki; tag[i] = tp; tag[p] = ti; }
+                const unsigned long long a = pk[i], b = pk[p];
+                if ((a > b) == ((i & k) == 0)) { pk[i] = b; pk[p] = a; }
             }
             __syncthreads();
+        }
+    }
+    // exact fix-up inside runs of equal (user, float image): odd-even transposition with fp64 (score, index) order
+    {
+        int round = 0;
+        for (;;) {
+            int swapped = 0;
+            for (int phase = 0; phase < 2; ++phase) {
+                for (int i = 2 * tid + phase; i + 1 < ne; i += 2 * TH) {
+                    const unsigned long long a = pk[i], b = pk[i + 1];
+                    if ((a >> 13) == (b >> 13)) {
+                        const int ia = (int)(a & 0x1FFFu), ib = (int)(b & 0x1FFFu);
+                        const double ka = keys[ia], kb = keys[ib];
+                        if (ka > kb || (ka == kb && ia > ib)) { pk[i] = b; pk[i + 1] = a; swapped = 1; }
+                    }
+                }
+                __syncthreads();
+            }
+            if (!__syncthreads_or(swapped)) break;
+            if (++round >= 48) { if (tid == 0) s_fallback = 1; break; }
+        }
+        __syncthreads();
+    }
+    const bool fallback = s_fallback != 0;
+    // tag[] = (user, source index) of every sorted slot; keys[] <- fp64 scores in sorted order
+    double srt[TE];
+#pragma unroll
+    for (int q = 0; q < TE; ++q) {
+        const int i = tid + q * TH;
+        srt[q] = CUDART_INF;
+        if (i < ne && !fallback) srt[q] = keys[(int)(pk[i] & 0x1FFFu)];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < TE; ++q) {
+        const int i = tid + q * TH;
+        if (i < np2) {
+            if (!fallback) {
+                if (i < ne) { keys[i] = srt[q]; tag[i] = ((uint32_t)ts.ul[i] << 16) | (uint32_t)(pk[i] & 0x1FFFu); }
+            } else {
+                keys[i] = r_m[q];
+                tag[i] = i < ne ? (((uint32_t)r_u[q] << 16) | (uint32_t)i) : 0xFFFFFFFFu;
+            }
+        }
+    }
+    __syncthreads();
+    if (fallback) {
+        // exact bitonic network on the composite key (user, fp64 score, index)
+        for (int k = 2; k <= np2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (np2 >> 1); t += TH) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int p = i | j;
+                    const bool asc = (i & k) == 0;
+                    const uint32_t ti = tag[i], tp = tag[p];
+                    const double ki = keys[i], kp = keys[p];
+                    const bool gt = ((ti >> 16) != (tp >> 16)) ? (ti > tp) : ((ki > kp) || (ki == kp && ti > tp));
+                    if (gt == asc) { keys[i] = kp; keys[p] = ki; tag[i] = tp; tag[p] = ti; }
+                }
+                __syncthreads();
+            }
         }
     }
     // sorted outputs: users stay in place (the user is the major key), scores ascending inside each user
@@ -537,7 +609,7 @@ __global__ void __launch_bounds__(TH) tile_sweep_kernel(const int32_t *__restric
     }
 }
 
-static size_t prepare_smem(int T, int cap) { return (size_t)cap * 8 + (size_t)T * (cap + TILE_MAX_USERS) * 4 + (size_t)cap * 4 + 2 * (size_t)cap; }
+static size_t prepare_smem(int T, int cap) { return (size_t)cap * 16 + (size_t)T * (cap + TILE_MAX_USERS) * 4 + (size_t)cap * 4 + 2 * (size_t)cap; }
 static size_t sweep_smem(int T, int cap) { return (size_t)T * (cap + TILE_MAX_USERS) * 8 + (size_t)cap * 8 + cap; }
 
 template <typename K>
