@@ -18,7 +18,7 @@ import numpy as np
 from .data import Ratings
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprimalcr_b200.so")
+LIB_PATH = os.environ.get("PRIMALCR_LIB") or os.path.join(_HERE, "libprimalcr_b200.so")   # PRIMALCR_LIB: A/B builds
 
 CCDR1, PCR, PCRPP = 0, 1, 2   # pmf.h:6
 

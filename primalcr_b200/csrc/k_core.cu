@@ -19,6 +19,14 @@ namespace pcr {
 
 #define FULL 0xffffffffu
 
+// minimum resident CTAs per SM requested from ptxas for the two N*k kernels (register budget = 65536 / (256 * MINB))
+#ifndef PCR_ROWSUM_MINB
+#define PCR_ROWSUM_MINB 4
+#endif
+#ifndef PCR_DOTS_MINB
+#define PCR_DOTS_MINB 3
+#endif
+
 #define LAUNCH(ctx, name, bytes, kernel, grid, block, smem, ...)                         \
     do {                                                                                 \
         (ctx).prof->begin(name, (ctx).stream, (double)(bytes));                          \
@@ -146,7 +154,7 @@ void k_dots(Ctx &c, const double *P, const int32_t *prow, const double *Q, const
 // stays in registers, the 32 item indices of a batch are fetched with one coalesced load, and the NC 16-byte loads of
 // a rating's Q row are issued back to back before the first FMA (NC is a template parameter => fully unrolled).
 template <int G, int NC>
-__global__ void __launch_bounds__(256, 3) dots_units_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
+__global__ void __launch_bounds__(256, PCR_DOTS_MINB) dots_units_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
                                                          const i64 *__restrict__ un_end,
                                                          i64 n_units, unsigned long long *__restrict__ ticket,
                                                          const double *__restrict__ P,
@@ -226,7 +234,7 @@ bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 
 // ------------------------------------------------------------------ K4: segmented weighted row sums
 
 template <int NCH>
-__global__ void __launch_bounds__(256) rowsum_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
+__global__ void __launch_bounds__(256, PCR_ROWSUM_MINB) rowsum_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
                                                      const i64 *__restrict__ un_end,
                                                      i64 n_units, unsigned long long *__restrict__ ticket,
                                                      const int32_t *__restrict__ ridx,
