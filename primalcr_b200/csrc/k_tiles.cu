@@ -148,8 +148,11 @@ __device__ __forceinline__ bool tile_users(TileShared<TH * TE> &ts, int first_us
 }
 
 // ---------------------------------------------------------------- tile_prepare: sort + windows + counts
+#ifndef PCR_PREP_MINB
+#define PCR_PREP_MINB 4
+#endif
 template <int TT, int TH>
-__global__ void __launch_bounds__(TH) tile_prepare_kernel(const int32_t *__restrict__ tile_first,
+__global__ void __launch_bounds__(TH, TH == 256 ? PCR_PREP_MINB : 1) tile_prepare_kernel(const int32_t *__restrict__ tile_first,
                                                           const int32_t *__restrict__ tile_nusers,
                                                           const i64 *__restrict__ tile_e0, const int32_t *__restrict__ tile_ne,
                                                           const uint8_t *__restrict__ active,
@@ -356,8 +359,11 @@ __global__ void __launch_bounds__(TH) tile_prepare_kernel(const int32_t *__restr
 // of ONE running prefix G over the user: S_t(x) = G[B_t + C_t(x)] - G[B_t].  A scalar segmented scan replaces the
 // T-vector scan of tile_sweep_kernel, and the look-up positions B_t + C_t(ub|lb) were stored by tile_prepare:
 //   acc_j = sum_{t>l} (G[idx_t] - G[B_t]) + sum_{t<l} (G[B_{t+1}] - G[idx_t]) = K_u[l] + sum_{t>l} G[idx_t] - sum_{t<l} G[idx_t]
+#ifndef PCR_LM_MINB
+#define PCR_LM_MINB 4
+#endif
 template <int MODE, int TT, int TH>
-__global__ void __launch_bounds__(TH) tile_lm_sweep_kernel(const int32_t *__restrict__ tile_first,
+__global__ void __launch_bounds__(TH, TH == 256 ? PCR_LM_MINB : 1) tile_lm_sweep_kernel(const int32_t *__restrict__ tile_first,
                                                            const int32_t *__restrict__ tile_nusers,
                                                            const i64 *__restrict__ tile_e0, const int32_t *__restrict__ tile_ne,
                                                            const uint8_t *__restrict__ active,

@@ -28,13 +28,18 @@ def run(shape, scale, k, solver, iters, lam=5000.0, check_pcr=False):
     t = time.time(); e.set_train(ds.train); e.set_factors(U, V); setup = time.time() - t
     objs = [e.initial_objective()]
     times, counters = [], []
-    for _ in range(iters):
+    for it in range(iters):
+        if it == iters - 1:
+            e.profile_enable(True); e.profile_reset()
         t = time.time(); objs.append(e.outer_iteration()); times.append(time.time() - t); counters.append(e.counters())
+    prof = e.profile(); e.profile_enable(False)
+    top = sorted(((v["ms"], n, v["launches"]) for n, v in prof.items()), reverse=True)[:12]
     recomputed = e.initial_objective()
     out = dict(shape=shape, scale=scale, solver=solver, k=k, d1=ds.d1, d2=ds.d2, nnz=ds.train.nnz,
                max_len=int(ds.train.lens().max()), gen_s=gen, setup_s=setup, sec_per_iter=times, objective=objs,
                recomputed_rel_err=abs(recomputed - objs[-1]) / abs(objs[-1]), monotone=bool(np.all(np.diff(objs) < 0)),
-               device_gb=e.device_bytes() / 1e9, counters=counters[-1])
+               device_gb=e.device_bytes() / 1e9, counters=counters[-1],
+               kernels_last_iter=[dict(name=n, ms=round(ms, 2), launches=l) for ms, n, l in top])
     if check_pcr:
         Ug, Vg = e.get_factors()
         e1 = api.Engine(api.Parameter(solver_type=3 - solver, k=k, lambda_=lam, maxiter=1, do_predict=0))
