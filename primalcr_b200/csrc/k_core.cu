@@ -406,31 +406,47 @@ __global__ void __launch_bounds__(TMA_WARPS * 32, 1) rowsum_tma_kernel(const int
     }
 }
 
-// out[seg] = lambda*x[seg] + partial[first unit] + partial[second unit] + ...   (fixed order)
+// out[seg] = lambda*x[seg] + partial[first unit] + partial[second unit] + ...   (fixed order => deterministic)
+// One warp per segment; a lane owns up to 4 double2 chunks of the row and walks the unit list once with all of them in
+// flight (16-byte loads).  kp = payload columns (even), the padding up to ld is kept exactly zero.
 __global__ void __launch_bounds__(256) rowsum_finalize_kernel(const i64 *__restrict__ seg_unit_ptr,
                                                               const int32_t *__restrict__ seg_unit_idx, i64 n_seg,
                                                               const double *__restrict__ partial, int ld,
                                                               const uint8_t *__restrict__ active, double lambda,
                                                               const double *__restrict__ x, double *__restrict__ out,
-                                                              int zero_if_empty, int kp /* payload columns, rest is padding */) {
+                                                              int zero_if_empty, int kp) {
     const int lane = threadIdx.x & 31;
     const i64 warp_global = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
     const i64 nwarps = ((i64)gridDim.x * 256) >> 5;
+    const int nch = kp >> 1, nch_ld = ld >> 1;
     for (i64 seg = warp_global; seg < n_seg; seg += nwarps) {
         if (active && !active[seg]) continue;
         const i64 u0 = seg_unit_ptr[seg], u1 = seg_unit_ptr[seg + 1];
-        for (int cidx = lane; cidx < ld; cidx += 32) {
-            if (cidx >= kp) { out[(size_t)seg * ld + cidx] = 0.0; continue; }      // keep the padding exactly zero
-            double v = (x != nullptr && !(zero_if_empty && u0 == u1)) ? lambda * x[(size_t)seg * ld + cidx] : 0.0;
-            i64 u = u0;
-            for (; u + 4 <= u1; u += 4) {       // 4 independent loads in flight, summed in unit order
-                double t[4];
+        const bool use_x = x != nullptr && !(zero_if_empty && u0 == u1);
+        double2 v[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) t[q] = partial[(size_t)(seg_unit_idx ? seg_unit_idx[u + q] : u + q) * ld + cidx];
-                v += t[0]; v += t[1]; v += t[2]; v += t[3];
+        for (int q = 0; q < 4; ++q) {
+            const int ci = lane + 32 * q;
+            v[q] = make_double2(0.0, 0.0);
+            if (use_x && ci < nch) {
+                const double2 xv = reinterpret_cast<const double2 *>(x + (size_t)seg * ld)[ci];
+                v[q] = make_double2(lambda * xv.x, lambda * xv.y);
             }
-            for (; u < u1; ++u) v += partial[(size_t)(seg_unit_idx ? seg_unit_idx[u] : u) * ld + cidx];
-            out[(size_t)seg * ld + cidx] = v;
+        }
+        for (i64 u = u0; u < u1; ++u) {
+            const double2 *prow = reinterpret_cast<const double2 *>(partial + (size_t)(seg_unit_idx ? seg_unit_idx[u] : u) * ld);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int ci = lane + 32 * q;
+                if (ci < nch) { const double2 t = prow[ci]; v[q].x += t.x; v[q].y += t.y; }
+            }
+        }
+        double2 *orow = reinterpret_cast<double2 *>(out + (size_t)seg * ld);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ci = lane + 32 * q;
+            if (ci < nch) orow[ci] = v[q];
+            else if (ci < nch_ld) orow[ci] = make_double2(0.0, 0.0);
         }
     }
 }
