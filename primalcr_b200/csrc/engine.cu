@@ -583,8 +583,8 @@ struct Engine {
     }
     // out[i] = lambda*x[i] + sum over user i of cbuf[e] * V[item(e)]   (U-side gradient / Hessian-vector product)
     void rowsum_users(const double *x, double *out, const uint8_t *active, int zero_if_empty) {
-        k_rowsum(ctx, X.un_seg, X.un_start, X.un_end, X.n_units, X.seg_unit_ptr, X.seg_unit_idx, d1, X.item, nullptr, cbuf, V, ld, active, partial,
-                 cfg.lambda, x, out, zero_if_empty, active ? 0.0 : pass_bytes(X.nnz, d1), k);
+        k_rowsum(ctx, X.un_seg, X.un_start, X.un_end, X.n_units, X.seg_unit_ptr, X.seg_unit_idx, d1, X.item, nullptr, cbuf, V, ld,
+                 active, partial, cfg.lambda, x, out, zero_if_empty, active ? 0.0 : pass_bytes(X.nnz, d1), k);
     }
 
     void require_ready() {
@@ -616,12 +616,17 @@ struct Engine {
     double update_V() {
         require_ready();
         const i64 vn = d2 * ld;
-        scores(U, V, m, nullptr); scores_valid = true; meta_valid = false;
-        if (cfg.solver == 2) prepare(m, nullptr);
+        // comp_m_new + get_sorted_mm (:417-418).  After an update_U the scores, the sorted state and the per-user losses of
+        // every user's LAST line-search trial are exactly those of the committed (U, V) -- same kernels, same inputs --
+        // so they are reused instead of being recomputed (update_U sets the three flags only when that holds).
+        if (!(scores_valid && (cfg.solver != 2 || meta_valid))) {
+            scores(U, V, m, nullptr); scores_valid = true; meta_valid = false; loss_matches_m = false;
+            if (cfg.solver == 2) prepare(m, nullptr);
+        }
         coeffs(0, nullptr);
         rowsum_items(V, g);
         // prev_obj = objective(m, U, V): m and the sorted state do not change during CG, so evaluate it now
-        user_losses(m, nullptr);
+        if (!loss_matches_m) user_losses(m, nullptr);
         const double prev_obj = total_objective(U, V);
         // ---- solve_delta(_new): pcrpp.cpp:335-358
         k_fill(ctx, delta, vn, 0.0);
@@ -677,8 +682,11 @@ struct Engine {
     // ------------------------------------------------------------------ update_U(_new), batched over users
     double update_U() {
         require_ready();
-        if (!scores_valid && !last_m_is_stale) { scores(U, V, m, nullptr); scores_valid = true; meta_valid = false; }
+        if (!scores_valid && !last_m_is_stale) { scores(U, V, m, nullptr); scores_valid = true; meta_valid = false; loss_matches_m = false; }
         if (cfg.solver == 2 && !meta_valid) prepare(m, nullptr);
+        // m holds scores(U, V) for every user (not the scores of a rejected V trial): then what the line search leaves
+        // behind is valid for the next update_V (see there)
+        const bool m_covers_all_users = scores_valid && cfg.solver == 2 && getenv("PRIMALCR_NO_REUSE") == nullptr;
         // gradient coefficients from m (stale m included, as precompute_ui / obtain_g_u do)
         coeffs(0, nullptr);
         // prev_obj: Primal-CR++ takes it from the same sorted state (objective_u_new :785); Primal-CR recomputes
@@ -719,7 +727,10 @@ struct Engine {
             if (n_ls == 0) break;
         }
         k_u_commit(ctx, us, U, d1, ld);
-        scores_valid = false; meta_valid = false; last_m_is_stale = false;
+        // Primal-CR++: every user that moved went through trial 0 at least, so m / the sorted state / us.loss are those
+        // of its last trial = its committed row; users that were skipped kept their row and their entries.
+        scores_valid = m_covers_all_users; meta_valid = m_covers_all_users; loss_matches_m = m_covers_all_users;
+        last_m_is_stale = false;
         // now_obj = sum_i obj_u + lambda/2 ||V||^2   (pcrpp.cpp:832-836)
         k_sum(ctx, us.obj_new, d1, red_partials, slots + 0);
         k_dot(ctx, V, V, d2 * ld, red_partials, slots + 1);

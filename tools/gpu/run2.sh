@@ -1,0 +1,18 @@
+cd $GRAFT_REPO_ROOT
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest17.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/pytest17.log
+run() { tag=$1; shift; env "$@" python tools/ab.py --tag $tag >> gpurun_out/ab2.jsonl 2>> gpurun_out/ab2.err; }
+rm -f gpurun_out/ab2.jsonl
+run hot0 PRIMALCR_HOT_ROWS=0
+run hot8 PRIMALCR_HOT_ROWS=8
+run hot16 PRIMALCR_HOT_ROWS=16
+run hot32 PRIMALCR_HOT_ROWS=32
+run hot64 PRIMALCR_HOT_ROWS=64
+run hot80 PRIMALCR_HOT_ROWS=80
+run hot128 PRIMALCR_HOT_ROWS=128
+python - <<'PY'
+import json
+for l in open('gpurun_out/ab2.jsonl'):
+    d=json.loads(l); k=d['kernels']
+    print(d['tag'], round(d['sec_per_iter'],4), 'dots',k.get('dots'),'dots_active',k.get('dots_active'),'rs_users_act',k.get('rowsum_users_active'),'rs_users',k.get('rowsum_users'), 'obj', d['objective'][-1])
+PY
