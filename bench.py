@@ -347,7 +347,7 @@ def main_ours(args):
                            "counters": its[-1]})
     kern = sorted(((v["ms"], n, v["launches"], v["bytes"]) for n, v in prof.items()), reverse=True)
     roof["kernels"] = [{"name": n, "ms_per_step": ms / args.steps, "launches_per_step": l / args.steps,
-                        "gbs": (b / (ms / 1e3) / 1e9 if b > 0 and ms > 0 else None)} for ms, n, l, b in kern[:12]]
+                        "gbs": (b / (ms / 1e3) / 1e9 if b > 0 and ms > 0 else None)} for ms, n, l, b in kern[:40]]
 
     cb = None
     if world == 1 and not args.no_cpu_baseline:

@@ -139,6 +139,24 @@ struct SortedMeta {          // per rating, in (user, ascending score) order
     i64 nnz = 0;                  // plane stride of lm_idx
 };
 
+// heavy users (more ratings than the largest tile) cut into chunks, all stages are grids over chunks (k_heavy.cu)
+static const int HEAVY_CHUNK = 2048;
+struct HeavyLM {
+    int n_users = 0, n_chunks = 0;
+    const int32_t *users = nullptr;        // [n_users] user id
+    const i64 *begin = nullptr, *end = nullptr;   // [n_users] absolute rating range of the user
+    const i64 *off = nullptr;              // [n_users] offset into the scratch arrays below (users are spaced len + 1 apart)
+    const int32_t *chunk_user = nullptr;   // [n_chunks] index into users[]
+    const int32_t *chunk_lo = nullptr;     // [n_chunks] first element of the chunk inside its user
+    const int32_t *chunk0 = nullptr;       // [n_users + 1] first chunk of every heavy user
+    int32_t *ccnt = nullptr;               // [n_chunks x 8] ratings per level of a chunk -> exclusive bases inside the user
+    int32_t *B = nullptr;                  // [n_users x 9] first level-major rank of every level (B[8] = len)
+    int32_t *idx = nullptr;                // [(T - 1) planes][htot] rank of the window end in every OTHER level
+    double *G = nullptr, *G2 = nullptr;    // [htot] running prefixes of the stream in level-major order
+    double *csum = nullptr;                // [n_chunks x 2] chunk sums
+    i64 htot = 0;
+};
+
 static const int TILE_CAP = 1024;        // ratings per tile of consecutive users (k_tiles.cu)
 static const int TILE_MAX_USERS = 128;   // users per tile
 static const int TILE_CAP_L = 4096;      // large tiles: 1024 threads

@@ -63,6 +63,8 @@ static int ceil4(int k) { return (k + 15) & ~15; }
 struct Engine {
     primalcr_config cfg;
     cudaStream_t stream = nullptr;
+    // side stream: the chunk-parallel heavy-user kernels (few, small grids) run beside the tile kernels of the same stage
+    cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; Ctx ctx_aux; bool use_aux = false;
     Profiler prof;
     DevPool pool;
     Ctx ctx;
@@ -84,8 +86,10 @@ struct Engine {
     SortedMeta meta;
     int32_t *iota = nullptr;
     bool scores_valid = false, meta_valid = false;
-    // heavy-user scratch
+    // heavy-user scratch of the one-CTA-per-user kernels (allocated on demand: T > 8, or the score-order outputs for tests)
     double *h_v = nullptr, *h_p1 = nullptr, *h_p2 = nullptr, *h_acc = nullptr; int32_t *h_cnt = nullptr;
+    HeavyLM hv;                       // chunk-parallel heavy-user path (k_heavy.cu)
+    bool heavy_chunked = false, heavy_windows_valid = false;
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     // V-side vectors [d2 x ld]
     double *g = nullptr, *delta = nullptr, *rr = nullptr, *p = nullptr, *Hp = nullptr, *Vnew = nullptr;
@@ -120,6 +124,10 @@ struct Engine {
         sms = prop.multiProcessorCount;
         PCR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         ctx.stream = stream; ctx.prof = &prof; ctx.sms = sms;
+        PCR_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+        PCR_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        PCR_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        use_aux = getenv("PRIMALCR_NO_AUX_STREAM") == nullptr;
         k = cfg.k; ld = ceil4(k);
         PCR_CUDA(cudaMallocHost(&h_slots, sizeof(double) * 32));
         PCR_CUDA(cudaMallocHost(&h_counters, sizeof(int) * 4));
@@ -128,12 +136,17 @@ struct Engine {
         red_partials = pool.alloc<double>(1024);
         us.counters = pool.alloc<int>(4);
         ctx.ticket = pool.alloc<unsigned long long>(1);
+        ctx_aux = ctx; ctx_aux.stream = aux;          // (the heavy-user kernels do not use the ticket counter)
         stats_dev = pool.alloc<i64>(8);
     }
     ~Engine() {
         cudaSetDevice(cfg.device);      // the communicator stays in the process-wide cache
+        if (aux) cudaStreamSynchronize(aux);
         if (stream) cudaStreamSynchronize(stream);
         prof.resolve();
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (aux) cudaStreamDestroy(aux);
         pool.release();
         if (h_slots) cudaFreeHost(h_slots);
         if (h_counters) cudaFreeHost(h_counters);
@@ -141,6 +154,10 @@ struct Engine {
         if (stream) cudaStreamDestroy(stream);
     }
     void bind() { PCR_CUDA(cudaSetDevice(cfg.device)); }
+    // heavy-user work of a stage goes to the side stream between fork and join (disjoint users => disjoint outputs)
+    bool heavy_on_aux() const { return use_aux && heavy_chunked && X.n_cls[2] > 0; }
+    void fork_aux() { PCR_CUDA(cudaEventRecord(ev_fork, stream)); PCR_CUDA(cudaStreamWaitEvent(aux, ev_fork, 0)); }
+    void join_aux() { PCR_CUDA(cudaEventRecord(ev_join, aux)); PCR_CUDA(cudaStreamWaitEvent(stream, ev_join, 0)); }
     void sync() { PCR_CUDA(cudaStreamSynchronize(stream)); prof.resolve(); }
 
     template <typename Tp> Tp *upload(const Tp *h, size_t n) {
@@ -295,9 +312,26 @@ struct Engine {
         for (int q = 0; q < 3; ++q) { X.n_cls[q] = (int)cls[q].size(); X.cls_users[q] = upload_vec(cls[q]); }
         X.heavy_off = upload_vec(hoff); X.heavy_total = htot;
         X.heavy_begin = upload_vec(hb); X.heavy_end = upload_vec(he);
-        h_v = pool.alloc<double>((size_t)htot); h_p1 = pool.alloc<double>((size_t)htot);
-        h_p2 = pool.alloc<double>((size_t)htot); h_acc = pool.alloc<double>((size_t)htot);
-        h_cnt = pool.alloc<int32_t>((size_t)htot);
+        heavy_chunked = use_tiles && getenv("PRIMALCR_NO_LM") == nullptr && getenv("PRIMALCR_HEAVY_LEGACY") == nullptr && !cls[2].empty();
+        if (heavy_chunked) {
+            std::vector<i64> hoff_h; std::vector<int32_t> cu, clo, c0;
+            for (size_t q = 0; q < cls[2].size(); ++q) {
+                hoff_h.push_back(hoff[cls[2][q]]);
+                c0.push_back((int32_t)cu.size());
+                for (i64 lo = 0; lo < he[q] - hb[q]; lo += HEAVY_CHUNK) { cu.push_back((int32_t)q); clo.push_back((int32_t)lo); }
+            }
+            c0.push_back((int32_t)cu.size());
+            hv.n_users = (int)cls[2].size(); hv.n_chunks = (int)cu.size(); hv.htot = htot;
+            hv.users = X.cls_users[2]; hv.begin = X.heavy_begin; hv.end = X.heavy_end;
+            hv.off = upload_vec(hoff_h); hv.chunk_user = upload_vec(cu); hv.chunk_lo = upload_vec(clo); hv.chunk0 = upload_vec(c0);
+            hv.ccnt = pool.alloc<int32_t>((size_t)hv.n_chunks * 8); hv.B = pool.alloc<int32_t>((size_t)hv.n_users * 9);
+            hv.idx = pool.alloc<int32_t>((size_t)std::max(T - 1, 1) * (size_t)htot);
+            hv.G = pool.alloc<double>((size_t)htot); hv.G2 = pool.alloc<double>((size_t)htot);
+            hv.csum = pool.alloc<double>((size_t)hv.n_chunks * 2);
+            sync();
+        } else {
+            alloc_heavy_legacy();
+        }
         // ---- row-sum work units over the CSR
         const double blk_bytes = getenv("PRIMALCR_UBLOCK_MB") ? atof(getenv("PRIMALCR_UBLOCK_MB")) * 1e6 : 24e6;
         const double v_bytes = (double)d2 * ld * 8.0;
@@ -361,6 +395,13 @@ struct Engine {
         {
             const double u_bytes = (double)d1 * ld * 8.0;
             int nb = (int)std::ceil(u_bytes / blk_bytes);
+            // ... but never so many blocks that an (item, user block) unit averages fewer than ~32 ratings: with many
+            // items (Yahoo / power-law shapes, d2 >= 500 k) the tiny units and their partial rows cost more than the L2
+            // misses of a larger block (measured: 24 MB -> ~100 MB blocks, -8 % per iteration on both shapes)
+            if (getenv("PRIMALCR_UBLOCK_MB") == nullptr) {
+                const i64 nb_max = std::max<i64>(1, nnz / (32 * std::max<i64>(d2, 1)));
+                if (nb > nb_max) nb = (int)nb_max;
+            }
             if (nb < 1) nb = 1;
             if (nb > 64) nb = 64;
             const i64 bu = (d1 + nb - 1) / nb > 0 ? (d1 + nb - 1) / nb : 1;
@@ -434,6 +475,21 @@ struct Engine {
         has_train = true;
     }
 
+    void alloc_heavy_legacy() {
+        if (h_v != nullptr || X.heavy_total <= 0) return;
+        const size_t htot = (size_t)X.heavy_total;
+        h_v = pool.alloc<double>(htot); h_p1 = pool.alloc<double>(htot);
+        h_p2 = pool.alloc<double>(htot); h_acc = pool.alloc<double>(htot);
+        h_cnt = pool.alloc<int32_t>(htot);
+    }
+    // score-order window pointers / counters of the heavy users: only the stage entry points read them when the
+    // chunk-parallel path is on (the sweeps use the level-major ranks)
+    void ensure_heavy_windows() {
+        if (!heavy_chunked || heavy_windows_valid || X.n_cls[2] == 0) return;
+        alloc_heavy_legacy();
+        k_windows(ctx, 2, X.cls_users[2], X.n_cls[2], nullptr, X.row_ptr, meta, T, X.heavy_off, h_cnt);
+        heavy_windows_valid = true;
+    }
     i64 ev_cap_pt = 0, ev_cap_d1 = 0, ev_cap_nnz = 0;
     void ensure_eval_buffers(const DevCsr &C) {
         if (C.n_pt > ev_cap_pt) { ev_err_item = pool.alloc<i64>((size_t)C.n_pt); ev_cap_pt = C.n_pt; }
@@ -527,26 +583,44 @@ struct Engine {
     }
     // get_sorted_mm + window pointers for every (active) user
     void prepare(const double *sc, const uint8_t *active) {
+        const bool par = heavy_on_aux();
+        Ctx &hc = par ? ctx_aux : ctx;
+        if (par) fork_aux();
+        if (X.n_cls[2] > 0) {
+            k_heavy_sort(hc, pool, &cub_tmp, &cub_tmp_bytes, sc, iota, meta.s, meta.pos, X.nnz, X.n_cls[2], X.heavy_begin, X.heavy_end);
+            k_gather_level(hc, X.cls_users[2], X.n_cls[2], nullptr, X.row_ptr, X.level, meta);
+            if (heavy_chunked) k_heavy_prepare(hc, hv, meta, T);
+        }
         for (int gq = 0; gq < 2; ++gq) k_tile_prepare(ctx, X, gq, active, sc, meta, T);
         k_sort_users(ctx, 0, X.cls_users[0], X.n_cls[0], active, X.row_ptr, sc, X.level, meta);
         k_sort_users(ctx, 1, X.cls_users[1], X.n_cls[1], active, X.row_ptr, sc, X.level, meta);
-        if (X.n_cls[2] > 0) {
-            k_heavy_sort(ctx, pool, &cub_tmp, &cub_tmp_bytes, sc, iota, meta.s, meta.pos, X.nnz, X.n_cls[2], X.heavy_begin, X.heavy_end);
-            k_gather_level(ctx, X.cls_users[2], X.n_cls[2], nullptr, X.row_ptr, X.level, meta);
-        }
-        for (int q = 0; q < 3; ++q)
+        for (int q = 0; q < 3; ++q) {
+            if (q == 2 && heavy_chunked) continue;
             k_windows(ctx, q, X.cls_users[q], X.n_cls[q], q == 2 ? nullptr : active, X.row_ptr, meta, T, X.heavy_off, h_cnt);
+        }
+        if (par) join_aux();
+        heavy_windows_valid = false;
         meta_valid = true;
     }
     void sweep_coeff(int mode, const uint8_t *active, const double *bsrc) {
+        const bool par = heavy_on_aux();
+        if (par) { fork_aux(); k_heavy_sweep(ctx_aux, mode, hv, active, meta, bsrc, cbuf, nullptr, T); }
         for (int gq = 0; gq < 2; ++gq) k_tile_sweep(ctx, mode, X, gq, active, meta, bsrc, cbuf, nullptr, T);
-        for (int q = 0; q < 3; ++q)
+        if (par) join_aux();
+        for (int q = 0; q < 3; ++q) {
+            if (q == 2 && heavy_chunked) { if (!par) k_heavy_sweep(ctx, mode, hv, active, meta, bsrc, cbuf, nullptr, T); continue; }
             k_sweep_coeff(ctx, q, mode, X.cls_users[q], X.n_cls[q], active, X.row_ptr, meta, bsrc, cbuf, T, X.heavy_off, h_v, h_p1, h_acc);
+        }
     }
     void sweep_obj(const uint8_t *active) {
+        const bool par = heavy_on_aux();
+        if (par) { fork_aux(); k_heavy_sweep(ctx_aux, 2, hv, active, meta, nullptr, nullptr, us.loss, T); }
         for (int gq = 0; gq < 2; ++gq) k_tile_sweep(ctx, 2, X, gq, active, meta, nullptr, nullptr, us.loss, T);
-        for (int q = 0; q < 3; ++q)
+        if (par) join_aux();
+        for (int q = 0; q < 3; ++q) {
+            if (q == 2 && heavy_chunked) { if (!par) k_heavy_sweep(ctx, 2, hv, active, meta, nullptr, nullptr, us.loss, T); continue; }
             k_sweep_obj(ctx, q, X.cls_users[q], X.n_cls[q], active, X.row_ptr, meta, us.loss, T, X.heavy_off, h_p1, h_p2, h_acc);
+        }
     }
     // per-user losses of the current scores `sc` into us.loss (both solvers)
     void user_losses(const double *sc, const uint8_t *active) {
@@ -1028,6 +1102,7 @@ int primalcr_sort_segments(primalcr_engine *e, double *sorted, int32_t *perm, in
     PCR_REQUIRE(E->cfg.solver == 2, "sorted state exists only for Primal-CR++");
     E->ensure_scores();
     E->prepare(E->m, nullptr);
+    E->ensure_heavy_windows();
     E->sync();
     const size_t n = (size_t)E->X.nnz;
     if (n) {
@@ -1057,6 +1132,7 @@ int primalcr_level_counts(primalcr_engine *e, int32_t *cnt_left, int32_t *cnt_ri
     E->require_ready();
     PCR_REQUIRE(E->cfg.solver == 2, "sorted state exists only for Primal-CR++");
     E->ensure_meta();
+    E->ensure_heavy_windows();
     const size_t n = (size_t)E->X.nnz * E->T;
     int32_t *dl = nullptr, *dr = nullptr;
     PCR_CUDA(cudaMalloc(&dl, sizeof(int32_t) * (n ? n : 1)));

@@ -11,13 +11,16 @@
 //   u_*         K6  per-user truncated Newton-CG bookkeeping update_u_new :779-815, solve_delta_u_new :628-647
 //   vec         K5  CG vector algebra of solve_delta_new :335-358
 #include "kernels.h"
+#include "block_prims.cuh"
 #include <math_constants.h>
 #include <algorithm>
 #include <cstdlib>
 
 namespace pcr {
 
+#ifndef FULL
 #define FULL 0xffffffffu
+#endif
 
 // minimum resident CTAs per SM requested from ptxas for the two N*k kernels (register budget = 65536 / (256 * MINB))
 #ifndef PCR_ROWSUM_MINB
@@ -52,55 +55,6 @@ static unsigned resident_grid(K kernel, int block, size_t smem, int sms, i64 max
     if (g > max_useful) g = max_useful;
     if (g < 1) g = 1;
     return (unsigned)g;
-}
-
-// ------------------------------------------------------------------ block primitives
-
-// a[0..n) -> exclusive prefix sums in place, a[n] = total.  Fixed summation tree => deterministic.
-// All threads call; caller synchronises before; ends with __syncthreads().
-template <typename T, int THREADS>
-__device__ __forceinline__ void block_excl_scan(T *a, int n, T *wsum /* [THREADS/32 + 1] shared */) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int chunk = (n + THREADS - 1) / THREADS;
-    int lo = tid * chunk; if (lo > n) lo = n;
-    int hi = lo + chunk;  if (hi > n) hi = n;
-    T local = 0;
-    for (int q = lo; q < hi; ++q) local += a[q];
-    T incl = local;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        T w = lane < THREADS / 32 ? wsum[lane] : (T)0;
-        T wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; }
-        if (lane < THREADS / 32) wsum[lane] = wi - w;
-        if (lane == 31) wsum[THREADS / 32] = wi;
-    }
-    __syncthreads();
-    T run = wsum[warp] + (incl - local);
-    for (int q = lo; q < hi; ++q) { T v = a[q]; a[q] = run; run += v; }
-    if (tid == 0) a[n] = wsum[THREADS / 32];
-    __syncthreads();
-}
-
-template <int THREADS>
-__device__ __forceinline__ double block_sum(double v, double *wsum /* [THREADS/32] shared */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    __syncthreads();
-    if (lane == 0) wsum[warp] = v;
-    __syncthreads();
-    double r = 0;
-    if (warp == 0) {
-        r = lane < THREADS / 32 ? wsum[lane] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
-    }
-    return r;   // valid in warp 0
 }
 
 // ------------------------------------------------------------------ K1: dots
@@ -258,6 +212,8 @@ __global__ void __launch_bounds__(256, PCR_ROWSUM_MINB) rowsum_kernel(const int3
             int ri = 0; double wi = 0.0;
             if (me < e) { ri = ridx[me]; wi = widx ? w[widx[me]] : w[me]; }
             const int cnt = (e - base) < 32 ? (int)(e - base) : 32;
+            // (measured: requesting the NEXT batch's ids / weights one batch ahead costs 8 registers and is slower: item-major
+            //  pass 5.8 -> 6.3 ms, dots 4.23 -> 4.29 ms)
             // (measured: forcing 8 or 16 loads per lane in flight with an explicit load-then-FMA batch costs more in
             //  occupancy than it gains -- 89 ms and 206 ms vs 73 ms per step for the item-major pass; the compiler's own
             //  interleaving of this 4x unrolled loop at 56 registers is the fastest variant)

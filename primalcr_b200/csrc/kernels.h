@@ -89,6 +89,13 @@ void k_tile_prepare(Ctx &c, const DevCsr &X, int geo, const uint8_t *active, con
 void k_tile_sweep(Ctx &c, int mode, const DevCsr &X, int geo, const uint8_t *active, const SortedMeta &meta, const double *b,
                   double *c_out, double *obj_user, int T);
 
+// ---------------------------------------------------------------- k_heavy.cu (users longer than a tile, chunk-parallel)
+// after k_heavy_sort + k_gather_level: level-major copy, window ranks and counters of every heavy user
+void k_heavy_prepare(Ctx &c, const HeavyLM &h, SortedMeta &meta, int T);
+// mode 0 gradient coefficient, 1 Hv coefficient (stream b), 2 per-user loss
+void k_heavy_sweep(Ctx &c, int mode, const HeavyLM &h, const uint8_t *active, const SortedMeta &meta, const double *b,
+                   double *c_out, double *obj_user, int T);
+
 // ---------------------------------------------------------------- k_pairs.cu (Primal-CR pair kernels, evaluation)
 // mode 0: gradient coefficient, 1: Hv coefficient (needs b), 2: objective partial per work item
 void k_pairs(Ctx &c, int mode, const DevCsr &X, const uint8_t *active, const double *m, const double *b,
