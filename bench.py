@@ -309,6 +309,13 @@ def main_ours(args):
     h2d = (h_rp.numel() * 8 + h_it.numel() * 4 + h_ra.numel() * 8 + h_U.numel() * 8 + h_V.numel() * 8) / args.steps
     d2h = (outU.numel() * 8 + outV.numel() * 8) / args.steps
 
+    per_rank = None
+    if world > 1:      # per-rank kernel totals (load balance of the user shards), gathered before the ranks part ways
+        mine = {"nnz": int(shard.nnz), "users": int(u1 - u0), "sec": ev0.elapsed_time(ev1) / 1e3 / args.steps,
+                "kernels": {n: round(v["ms"] / args.steps, 3) for n, v in prof.items() if v["ms"] / args.steps >= 0.05}}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -363,7 +370,7 @@ def main_ours(args):
         "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "whole pcrpp()-style call (upload CSR+U+V, build CSC, %d iterations, download U+V) / iterations" % args.steps},
         "gpu_launches": int(launches),
-        "roofline": roof, "cpu_baseline": cb,
+        "roofline": roof, "cpu_baseline": cb, "per_rank": per_rank,
         "objective": objs, "device_bytes": dev_bytes,
     }
     _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
