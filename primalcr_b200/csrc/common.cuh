@@ -132,11 +132,15 @@ struct SortedMeta {          // per rating, in (user, ascending score) order
     int32_t *ub = nullptr, *lb = nullptr;      // window pointers (local to the user)
     int32_t *cnt_lo = nullptr, *cnt_hi = nullptr;
     // level-major copy for the users served by tiles: per rating in (user, level, ascending score) order
-    double *lm_s = nullptr; int32_t *lm_pos = nullptr; uint8_t *lm_lev = nullptr;
-    int32_t *lm_lo = nullptr, *lm_hi = nullptr;
-    uint16_t *lm_idx = nullptr;   // [(T-1) planes][nnz]: rank (inside the user, level-major) of the window end in every OTHER level
+    // (heavy users keep their own 32-bit arrays, HeavyLM; only lm_s is shared with them)
+    double *lm_s = nullptr;
+    // packed record of a tile user's rating, 13-bit fields (a tile holds <= 4096 ratings):
+    //   lm_w0 = pos - tile_e0 | cnt_lo << 13 | cnt_hi << 26 | level << 39 | user index inside the tile << 42
+    //   lm_w1 = rank (inside the user, level-major) of the window end in the 1st..4th OTHER level, 13 bits each
+    //   lm_w2 = the same for the 5th..7th other level (only allocated when T > 5)
+    unsigned long long *lm_w0 = nullptr, *lm_w1 = nullptr, *lm_w2 = nullptr;
     uint16_t *ulev = nullptr;     // [d1][8] ratings per level of every user
-    i64 nnz = 0;                  // plane stride of lm_idx
+    i64 nnz = 0;
 };
 
 // heavy users (more ratings than the largest tile) cut into chunks, all stages are grids over chunks (k_heavy.cu)
@@ -152,6 +156,8 @@ struct HeavyLM {
     int32_t *ccnt = nullptr;               // [n_chunks x 8] ratings per level of a chunk -> exclusive bases inside the user
     int32_t *B = nullptr;                  // [n_users x 9] first level-major rank of every level (B[8] = len)
     int32_t *idx = nullptr;                // [(T - 1) planes][htot] rank of the window end in every OTHER level
+    int32_t *pos = nullptr, *lo = nullptr, *hi = nullptr;   // [htot] level-major order: CSR position, aggregated counters
+    uint8_t *lev = nullptr;                // [htot] level-major order: level
     double *G = nullptr, *G2 = nullptr;    // [htot] running prefixes of the stream in level-major order
     double *csum = nullptr;                // [n_chunks x 2] chunk sums
     i64 htot = 0;

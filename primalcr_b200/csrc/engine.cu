@@ -327,6 +327,8 @@ struct Engine {
             hv.ccnt = pool.alloc<int32_t>((size_t)hv.n_chunks * 8); hv.B = pool.alloc<int32_t>((size_t)hv.n_users * 9);
             hv.idx = pool.alloc<int32_t>((size_t)std::max(T - 1, 1) * (size_t)htot);
             hv.G = pool.alloc<double>((size_t)htot); hv.G2 = pool.alloc<double>((size_t)htot);
+            hv.pos = pool.alloc<int32_t>((size_t)htot); hv.lo = pool.alloc<int32_t>((size_t)htot); hv.hi = pool.alloc<int32_t>((size_t)htot);
+            hv.lev = pool.alloc<uint8_t>((size_t)htot);
             hv.csum = pool.alloc<double>((size_t)hv.n_chunks * 2);
             sync();
         } else {
@@ -443,10 +445,9 @@ struct Engine {
         meta.cnt_lo = pool.alloc<int32_t>((size_t)nnz); meta.cnt_hi = pool.alloc<int32_t>((size_t)nnz);
         meta.nnz = nnz;
         if (use_tiles && getenv("PRIMALCR_NO_LM") == nullptr) {     // level-major copy for the tile users
-            meta.lm_s = pool.alloc<double>((size_t)nnz); meta.lm_pos = pool.alloc<int32_t>((size_t)nnz);
-            meta.lm_lev = pool.alloc<uint8_t>((size_t)nnz);
-            meta.lm_lo = pool.alloc<int32_t>((size_t)nnz); meta.lm_hi = pool.alloc<int32_t>((size_t)nnz);
-            meta.lm_idx = pool.alloc<uint16_t>((size_t)nnz * (size_t)std::max(T - 1, 1));
+            meta.lm_s = pool.alloc<double>((size_t)nnz);
+            meta.lm_w0 = pool.alloc<unsigned long long>((size_t)nnz); meta.lm_w1 = pool.alloc<unsigned long long>((size_t)nnz);
+            if (T > 5) meta.lm_w2 = pool.alloc<unsigned long long>((size_t)nnz);
             meta.ulev = pool.alloc<uint16_t>((size_t)d1 * 8);
             PCR_CUDA(cudaMemsetAsync(meta.ulev, 0, sizeof(uint16_t) * (size_t)d1 * 8, stream));
         }

@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(HTH) hv_scatter_lm_kernel(HeavyLM h, const dou
     __syncthreads();
     for (int i = tid; i < ci.cnt; i += HTH) {
         const i64 src = ci.start + ci.lo + i, dst = ci.start + srank[i];
-        lm.lm_s[dst] = s_sorted[src]; lm.lm_pos[dst] = pos_sorted[src]; lm.lm_lev[dst] = slev[i];
+        const i64 hd = ci.off + srank[i];
+        lm.lm_s[dst] = s_sorted[src]; h.pos[hd] = pos_sorted[src]; h.lev[hd] = slev[i];
     }
 }
 
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(HTH) hv_windows_lm_kernel(HeavyLM h, SortedMet
     for (int i = threadIdx.x; i < ci.cnt; i += HTH) {
         const int x = ci.lo + i;
         const double sj = ss[x];
-        const int l = lm.lm_lev[ci.start + x];
+        const int l = h.lev[ci.off + x];
         const double hi = __dadd_rn(sj, 1.0), lo = __dadd_rn(sj, -1.0);
         int chi = 0, clo = 0;
         for (int t = 0; t < T; ++t) {
@@ -160,17 +161,17 @@ __global__ void __launch_bounds__(HTH) hv_windows_lm_kernel(HeavyLM h, SortedMet
             else       { while (a < b) { const int mid = (a + b) >> 1; if (ss[mid] < lo) a = mid + 1; else b = mid; } clo += B[t + 1] - a; }
             h.idx[(size_t)(t < l ? t : t - 1) * h.htot + ci.off + x] = a;
         }
-        lm.lm_lo[ci.start + x] = clo; lm.lm_hi[ci.start + x] = chi;
+        h.lo[ci.off + x] = clo; h.hi[ci.off + x] = chi;
     }
 }
 
 // ---------------------------------------------------------------- sweep 1: chunk sums of the stream (level-major order)
 // MODE 0: v = s, MODE 1: v = b[pos], MODE 2: v = s - 1 and (s - 1)^2
 template <int MODE>
-__device__ __forceinline__ double hv_stream(const SortedMeta &lm, const double *__restrict__ b_g, i64 at) {
-    if (MODE == 1) return b_g[lm.lm_pos[at]];
-    if (MODE == 2) return lm.lm_s[at] - 1.0;
-    return lm.lm_s[at];
+__device__ __forceinline__ double hv_stream(const HeavyLM &h, const SortedMeta &lm, const double *__restrict__ b_g, const ChunkInfo &ci, int x) {
+    if (MODE == 1) return b_g[h.pos[ci.off + x]];
+    if (MODE == 2) return lm.lm_s[ci.start + x] - 1.0;
+    return lm.lm_s[ci.start + x];
 }
 
 template <int MODE>
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(HTH) hv_chunk_sums_kernel(HeavyLM h, const uin
     if (active && !active[ci.u]) return;
     double a = 0.0, a2 = 0.0;
     for (int i = threadIdx.x; i < ci.cnt; i += HTH) {
-        const double v = hv_stream<MODE>(lm, b_g, ci.start + ci.lo + i);
+        const double v = hv_stream<MODE>(h, lm, b_g, ci, ci.lo + i);
         a += v;
         if (MODE == 2) a2 += v * v;
     }
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(HTH) hv_chunk_scan_kernel(HeavyLM h, const uin
     const bool last = ci.lo + ci.cnt == ci.n;
     for (int pass = 0; pass < (MODE == 2 ? 2 : 1); ++pass) {
         for (int i = tid; i < ci.cnt; i += HTH) {
-            const double v = hv_stream<MODE>(lm, b_g, ci.start + ci.lo + i);
+            const double v = hv_stream<MODE>(h, lm, b_g, ci, ci.lo + i);
             a[i] = pass == 0 ? v : v * v;
         }
         __syncthreads();
@@ -248,7 +249,8 @@ __global__ void __launch_bounds__(HTH) hv_lookup_kernel(HeavyLM h, const uint8_t
     for (int i = threadIdx.x; i < ci.cnt; i += HTH) {
         const int x = ci.lo + i;
         const i64 at = ci.start + x;
-        const int l = lm.lm_lev[at];
+        const i64 ha = ci.off + x;
+        const int l = h.lev[ha];
         double acc = Kt[l], acc2 = MODE == 2 ? Kt2[l] : 0.0;
         for (int t = 0; t < T; ++t) {
             if (t == l) continue;
@@ -259,11 +261,11 @@ __global__ void __launch_bounds__(HTH) hv_lookup_kernel(HeavyLM h, const uint8_t
         }
         if (MODE == 2) {
             const double v = lm.lm_s[at];
-            part += (double)lm.lm_hi[at] * (v * v) - 2.0 * v * acc + acc2;
+            part += (double)h.hi[ha] * (v * v) - 2.0 * v * acc + acc2;
         } else {
-            const int pos = lm.lm_pos[at];
+            const int pos = h.pos[ha];
             const double v = MODE == 0 ? lm.lm_s[at] : b_g[pos];
-            const double lo = (double)lm.lm_lo[at], hi = (double)lm.lm_hi[at];
+            const double lo = (double)h.lo[ha], hi = (double)h.hi[ha];
             const double cc = MODE == 0 ? lo * (v - 1.0) + hi * (v + 1.0) - acc : (lo + hi) * v - acc;
             c_out[pos] = 2.0 * cc;
         }

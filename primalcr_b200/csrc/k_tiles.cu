@@ -338,11 +338,20 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_PREP_MINB : 1) tile_prepar
                 }
             }
             const i64 gi = e0 + u0 + r;
-            lm.lm_s[gi] = sj; lm.lm_pos[gi] = (int32_t)(e0 + (int)(tag[i] & 0xFFFFu)); lm.lm_lev[gi] = (uint8_t)l;
-            lm.lm_lo[gi] = clo; lm.lm_hi[gi] = chi;
+            unsigned long long w1 = 0ull, w2 = 0ull;
 #pragma unroll
-            for (int t = 0; t < TT; ++t)
-                if (t < T && t != l) lm.lm_idx[(i64)(t < l ? t : t - 1) * lm.nnz + gi] = other[t];
+            for (int t = 0; t < TT; ++t) {
+                if (t < T && t != l) {
+                    const int slot = t < l ? t : t - 1;
+                    if (slot < 4) w1 |= (unsigned long long)other[t] << (13 * slot);
+                    else          w2 |= (unsigned long long)other[t] << (13 * (slot - 4));
+                }
+            }
+            lm.lm_s[gi] = sj;
+            lm.lm_w0[gi] = (unsigned long long)(tag[i] & 0xFFFFu) | ((unsigned long long)clo << 13) | ((unsigned long long)chi << 26) |
+                           ((unsigned long long)l << 39) | ((unsigned long long)u << 42);
+            lm.lm_w1[gi] = w1;
+            if (TT > 5) lm.lm_w2[gi] = w2;
         }
     }
     if (lm.ulev != nullptr) {
@@ -390,29 +399,24 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_LM_MINB : 1) tile_lm_sweep
         if (!tile_users<TH>(ts, first_user, n_users, e0, row_ptr, active)) return;
         users_done = true;
     }
-    int r_pos[TE], r_lo[TE], r_hi[TE], r_u[TE];
-    uint8_t r_l[TE];
-    uint16_t r_idx[TE][TT - 1];
+    // one packed record per rating (see SortedMeta): two (T <= 5) or three 8-byte loads instead of nine scalar ones
+    unsigned long long r_w0[TE], r_w1[TE], r_w2[TT > 5 ? TE : 1];
     double r_v[TE];
 #pragma unroll
     for (int q = 0; q < TE; ++q) {
         const int i = tid + q * TH;
-        r_pos[q] = 0; r_lo[q] = 0; r_hi[q] = 0; r_u[q] = 0; r_l[q] = 0; r_v[q] = 0.0;
-#pragma unroll
-        for (int t = 0; t < TT - 1; ++t) r_idx[q][t] = 0;
+        r_w0[q] = 0ull; r_w1[q] = 0ull; r_v[q] = 0.0;
+        if (TT > 5) r_w2[q] = 0ull;
         if (i < ne) {
-            r_u[q] = user_of[e0 + i] - first_user;
-            r_l[q] = lm.lm_lev[e0 + i];
-            r_hi[q] = lm.lm_hi[e0 + i];
-            if (MODE != 2) { r_pos[q] = lm.lm_pos[e0 + i]; r_lo[q] = lm.lm_lo[e0 + i]; }
+            r_w0[q] = lm.lm_w0[e0 + i];
+            r_w1[q] = lm.lm_w1[e0 + i];
+            if (TT > 5) r_w2[q] = lm.lm_w2[e0 + i];
             if (MODE != 1) r_v[q] = lm.lm_s[e0 + i];
-#pragma unroll
-            for (int t = 0; t < TT - 1; ++t) if (t < T - 1) r_idx[q][t] = lm.lm_idx[(i64)t * lm.nnz + e0 + i];
         }
     }
     if (MODE == 1) {
 #pragma unroll
-        for (int q = 0; q < TE; ++q) { const int i = tid + q * TH; if (i < ne) r_v[q] = b_g[r_pos[q]]; }
+        for (int q = 0; q < TE; ++q) { const int i = tid + q * TH; if (i < ne) r_v[q] = b_g[e0 + (i64)(r_w0[q] & 0x1FFFull)]; }
     }
     if (!users_done) tile_users<TH>(ts, first_user, n_users, e0, row_ptr, active);
     // block starts of every user's levels (ranks inside the user)
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_LM_MINB : 1) tile_lm_sweep
 #pragma unroll
     for (int q = 0; q < TE; ++q) {
         const int i = tid + q * TH;
-        if (i < ne) { ts.ul[i] = (uint8_t)r_u[q]; sval[i] = MODE == 2 ? r_v[q] - 1.0 : r_v[q]; }
+        if (i < ne) { ts.ul[i] = (uint8_t)((r_w0[q] >> 42) & 0x7Full); sval[i] = MODE == 2 ? r_v[q] - 1.0 : r_v[q]; }
     }
     __syncthreads();
     tile_level_scan<double, 1, TH>(ts, ne, 1, G, wagg, wflag, [&](int i) { return sval[i]; }, [](int) { return 0; });
@@ -450,25 +454,28 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_LM_MINB : 1) tile_lm_sweep
         const int i = tid + q * TH;
         objj[q] = 0.0;
         if (i >= ne) continue;
-        const int u = r_u[q];
+        const unsigned long long w0 = r_w0[q];
+        const int u = (int)((w0 >> 42) & 0x7Full);
         if (!ts.uact[u]) continue;
-        const int base = ts.ustart[u] + u, l = r_l[q];
+        const int base = ts.ustart[u] + u, l = (int)((w0 >> 39) & 7ull);
         double acc = Kt[u * TT + l], acc2 = MODE == 2 ? Kt2[u * TT + l] : 0.0;
 #pragma unroll
         for (int t = 0; t < TT - 1; ++t) {
             if (t < T - 1) {
-                const int at = base + r_idx[q][t];
+                const unsigned long long wi = (TT > 5 && t >= 4) ? r_w2[TT > 5 ? q : 0] >> (13 * (t - 4)) : r_w1[q] >> (13 * t);
+                const int at = base + (int)(wi & 0x1FFFull);
                 if (t >= l) { acc += G[at]; if (MODE == 2) acc2 += G2[at]; }      // other level t+1 > l
                 else if (MODE != 2) acc -= G[at];                                    // other level t < l
             }
         }
         const double v = r_v[q];
+        const double hi = (double)(int)((w0 >> 26) & 0x1FFFull);
         if (MODE == 2) {
-            objj[q] = (double)r_hi[q] * (v * v) - 2.0 * v * acc + acc2;
+            objj[q] = hi * (v * v) - 2.0 * v * acc + acc2;
         } else {
-            const double lo = (double)r_lo[q], hi = (double)r_hi[q];
+            const double lo = (double)(int)((w0 >> 13) & 0x1FFFull);
             const double cc = MODE == 0 ? lo * (v - 1.0) + hi * (v + 1.0) - acc : (lo + hi) * v - acc;
-            c_out[r_pos[q]] = 2.0 * cc;
+            c_out[e0 + (i64)(w0 & 0x1FFFull)] = 2.0 * cc;
         }
     }
     if (MODE == 2) {
