@@ -299,12 +299,19 @@ def main_ours(args):
     barrier()
     t0 = time.perf_counter()
     e2 = new_engine(args.steps)
+    t1 = time.perf_counter()
     e2.set_train_raw(shard.d1, shard.d2, shard.nnz, h_rp, h_it, h_ra)
+    t2 = time.perf_counter()
     e2.set_factors(h_U, h_V)
+    t3 = time.perf_counter()
     e2.run(log=None)
+    t4 = time.perf_counter()
     e2.get_factors(outU, outV)
     barrier()
-    e2e_sec = max_over_ranks(time.perf_counter() - t0) / args.steps
+    t5 = time.perf_counter()
+    e2e_sec = max_over_ranks(t5 - t0) / args.steps
+    e2e_phases = {"create": t1 - t0, "set_train": t2 - t1, "set_factors": t3 - t2, "run": t4 - t3, "get_factors": t5 - t4}
+    log("[bench] rank %d e2e phases (s): %s" % (rank, {k_: round(v_, 4) for k_, v_ in e2e_phases.items()}))
     e2.close()
     h2d = (h_rp.numel() * 8 + h_it.numel() * 4 + h_ra.numel() * 8 + h_U.numel() * 8 + h_V.numel() * 8) / args.steps
     d2h = (outU.numel() * 8 + outV.numel() * 8) / args.steps
@@ -368,6 +375,7 @@ def main_ours(args):
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, ds),
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "phases_s": e2e_phases,
                 "note": "whole pcrpp()-style call (upload CSR+U+V, build CSC, %d iterations, download U+V) / iterations" % args.steps},
         "gpu_launches": int(launches),
         "roofline": roof, "cpu_baseline": cb, "per_rank": per_rank,

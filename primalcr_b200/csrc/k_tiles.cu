@@ -218,16 +218,62 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_PREP_MINB : 1) tile_prepar
     }
     if (tid == 0) s_fallback = 0;
     __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (np2 >> 1); t += TH) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int p = i | j;
-                const unsigned long long a = pk[i], b = pk[p];
-                if ((a > b) == ((i & k) == 0)) { pk[i] = b; pk[p] = a; }
+    // Bitonic network with BLOCKED ownership (thread t holds positions 4t..4t+3 in registers): the j = 1, 2 stages are
+    // register compare-exchanges, j = 4..64 are warp shuffles with lane ^ (j/4), and only j >= 128 (partner in another
+    // warp) goes through shared memory -- 6 of the 55 stages of a 1024-key tile.  (ncu on the all-shared-memory version:
+    // l1tex data-pipe wavefronts 87 % of peak, 137 M bank conflicts: the LDS/STS traffic of the network was the limit.)
+    {
+        const int p0 = tid * TE;
+        const bool live = ((tid & ~31) * TE) < np2;            // warp-uniform: this warp owns positions below np2
+        unsigned long long ek[TE];
+#pragma unroll
+        for (int q = 0; q < TE; ++q) ek[q] = pk[p0 + q];       // p0 + q < CAP always; entries >= np2 are never paired with < np2
+        for (int k = 2; k <= np2; k <<= 1) {
+            for (int j = k >> 1; j >= 32 * TE; j >>= 1) {      // partner thread lives in another warp
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < TE; ++q) pk[p0 + q] = ek[q];
+                __syncthreads();
+                const int m = j / TE;
+                const int pp = (tid ^ m) * TE;
+                const bool keep_min = (((tid & m) == 0) == ((p0 & k) == 0));
+#pragma unroll
+                for (int q = 0; q < TE; ++q) {
+                    const unsigned long long o = pk[pp + q];
+                    ek[q] = keep_min ? (o < ek[q] ? o : ek[q]) : (o > ek[q] ? o : ek[q]);
+                }
             }
-            __syncthreads();
+            if (live) {
+                const int jtop = (k >> 1) < 16 * TE ? (k >> 1) : 16 * TE;
+                for (int j = jtop; j >= TE; j >>= 1) {          // partner lane = lane ^ (j / TE)
+                    const int m = j / TE;
+                    const bool keep_min = (((tid & m) == 0) == ((p0 & k) == 0));
+#pragma unroll
+                    for (int q = 0; q < TE; ++q) {
+                        const unsigned long long o = __shfl_xor_sync(FULL, ek[q], m);
+                        ek[q] = keep_min ? (o < ek[q] ? o : ek[q]) : (o > ek[q] ? o : ek[q]);
+                    }
+                }
+                if (k >= 4) {                                   // j = 2: pairs (0,2), (1,3); direction is per thread for k >= 4
+                    const bool asc = ((p0 & k) == 0);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const unsigned long long a = ek[q], b = ek[q + 2];
+                        if ((a > b) == asc) { ek[q] = b; ek[q + 2] = a; }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < TE; q += 2) {               // j = 1: pairs (0,1), (2,3)
+                    const bool asc = (((p0 + q) & k) == 0);
+                    const unsigned long long a = ek[q], b = ek[q + 1];
+                    if ((a > b) == asc) { ek[q] = b; ek[q + 1] = a; }
+                }
+            }
         }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < TE; ++q) pk[p0 + q] = ek[q];
+        __syncthreads();
     }
     // exact fix-up inside runs of equal (user, float image): odd-even transposition with fp64 (score, index) order
     {
@@ -369,7 +415,7 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_PREP_MINB : 1) tile_prepar
 // T-vector scan of tile_sweep_kernel, and the look-up positions B_t + C_t(ub|lb) were stored by tile_prepare:
 //   acc_j = sum_{t>l} (G[idx_t] - G[B_t]) + sum_{t<l} (G[B_{t+1}] - G[idx_t]) = K_u[l] + sum_{t>l} G[idx_t] - sum_{t<l} G[idx_t]
 #ifndef PCR_LM_MINB
-#define PCR_LM_MINB 4
+#define PCR_LM_MINB 5      // measured with the packed records: 4 -> 21.2, 5 -> 18.5, 6 -> 19.8 ms per iteration (Hv sweeps)
 #endif
 template <int MODE, int TT, int TH>
 __global__ void __launch_bounds__(TH, TH == 256 ? PCR_LM_MINB : 1) tile_lm_sweep_kernel(const int32_t *__restrict__ tile_first,
