@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include <map>
@@ -67,14 +68,23 @@ struct Profiler {
         PCR_CUDA(cudaEventRecord(pending.back().b, s));
     }
     void resolve() {   // caller has synchronised the stream
+        // PRIMALCR_TRACE=<file>: one line per launch, "start_ms duration_ms name" (start relative to the first launch of the batch)
+        static const char *trace_path = getenv("PRIMALCR_TRACE");
+        FILE *tf = (trace_path && !pending.empty()) ? fopen(trace_path, "a") : nullptr;
         for (auto &r : pending) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
                 acc[r.id].ms += ms; acc[r.id].launches += 1; acc[r.id].bytes += r.bytes;
+                if (tf) {
+                    float t0 = 0;
+                    cudaEventElapsedTime(&t0, pending.front().a, r.a);
+                    fprintf(tf, "%.4f %.4f %s\n", t0, ms, acc[r.id].name.c_str());
+                }
             }
             pool.push_back(r.a); pool.push_back(r.b);
         }
         pending.clear();
+        if (tf) { fprintf(tf, "# batch end\n"); fclose(tf); }
     }
     void reset() { resolve(); for (auto &a : acc) { a.ms = 0; a.launches = 0; a.bytes = 0; } }
     ~Profiler() { for (auto &r : pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } for (auto e : pool) cudaEventDestroy(e); }

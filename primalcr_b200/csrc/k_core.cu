@@ -1021,11 +1021,19 @@ __global__ void __launch_bounds__(256) u_stats_kernel(UState s, const i64 *__res
         const i64 len = row_ptr[i + 1] - row_ptr[i];
         a += len * s.cg_its[i]; b += len * s.ls_trials[i]; sk += s.skipped[i]; ci += s.cg_its[i]; li += s.ls_trials[i];
     }
-    atomicAdd((unsigned long long *)&out8[3], (unsigned long long)a);
-    atomicAdd((unsigned long long *)&out8[4], (unsigned long long)b);
-    atomicAdd((unsigned long long *)&out8[5], (unsigned long long)sk);
-    atomicAdd((unsigned long long *)&out8[6], (unsigned long long)ci);
-    atomicAdd((unsigned long long *)&out8[7], (unsigned long long)li);
+    // warp-level sums first: one atomic per warp and counter instead of one per thread (0.5 ms -> a few microseconds)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); sk += __shfl_xor_sync(FULL, sk, o);
+        ci += __shfl_xor_sync(FULL, ci, o); li += __shfl_xor_sync(FULL, li, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd((unsigned long long *)&out8[3], (unsigned long long)a);
+        atomicAdd((unsigned long long *)&out8[4], (unsigned long long)b);
+        atomicAdd((unsigned long long *)&out8[5], (unsigned long long)sk);
+        atomicAdd((unsigned long long *)&out8[6], (unsigned long long)ci);
+        atomicAdd((unsigned long long *)&out8[7], (unsigned long long)li);
+    }
 }
 
 void k_u_init(Ctx &c, UState &s, const double *U, const i64 *row_ptr, const uint8_t *has_pairs, i64 d1, int ld, double lambda) {
