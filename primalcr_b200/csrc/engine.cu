@@ -123,8 +123,14 @@ struct Engine {
         PCR_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
         sms = prop.multiProcessorCount;
         PCR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        pool.init(stream);
         ctx.stream = stream; ctx.prof = &prof; ctx.sms = sms;
-        PCR_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+        {   // highest priority: the few CTAs of the heavy-user kernels are placed first whenever SM slots free up, so they finish
+            // inside the tile kernel that runs beside them instead of after it
+            int prio_lo = 0, prio_hi = 0;
+            PCR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            PCR_CUDA(cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, prio_hi));
+        }
         PCR_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         PCR_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         use_aux = getenv("PRIMALCR_NO_AUX_STREAM") == nullptr;
@@ -350,11 +356,11 @@ struct Engine {
             n_item_blocks = nb;
             std::vector<i64> bpos((size_t)d1 * (nb + 1));
             i64 *bpos_d = nullptr;
-            PCR_CUDA(cudaMalloc(&bpos_d, sizeof(i64) * std::max<size_t>(bpos.size(), 1)));
+            bpos_d = (i64 *)pool.raw_alloc(sizeof(i64) * std::max<size_t>(bpos.size(), 1));
             k_csc_block_bounds(ctx, X.row_ptr, X.item, d1, nb, bi, bpos_d);
             PCR_CUDA(cudaMemcpyAsync(bpos.data(), bpos_d, sizeof(i64) * bpos.size(), cudaMemcpyDeviceToHost, stream));
             sync();
-            cudaFree(bpos_d);
+            pool.raw_free(bpos_d);
             std::vector<int32_t> useg, uidx; std::vector<i64> ustart, uend, supt((size_t)d1 + 1, 0);
             useg.reserve((size_t)d1 * 4); ustart.reserve((size_t)d1 * 4); uend.reserve((size_t)d1 * 4);
             for (int blk = 0; blk < nb; ++blk)
@@ -410,11 +416,11 @@ struct Engine {
             n_user_blocks = nb;
             std::vector<i64> bpos((size_t)d2 * (nb + 1));
             i64 *bpos_d = nullptr;
-            PCR_CUDA(cudaMalloc(&bpos_d, sizeof(i64) * bpos.size()));
+            bpos_d = (i64 *)pool.raw_alloc(sizeof(i64) * bpos.size());
             k_csc_block_bounds(ctx, col_ptr, csc_user, d2, nb, bu, bpos_d);
             PCR_CUDA(cudaMemcpyAsync(bpos.data(), bpos_d, sizeof(i64) * bpos.size(), cudaMemcpyDeviceToHost, stream));
             sync();
-            cudaFree(bpos_d);
+            pool.raw_free(bpos_d);
             std::vector<int32_t> cseg, cidx; std::vector<i64> cstart, cend, csup((size_t)d2 + 1, 0);
             for (int blk = 0; blk < nb; ++blk)
                 for (i64 pcol = 0; pcol < d2; ++pcol) {
@@ -516,11 +522,11 @@ struct Engine {
             PCR_CUDA(cudaMemcpyAsync(dst, h, sizeof(double) * (size_t)rows * k, cudaMemcpyHostToDevice, stream));
         } else {
             double *tmp = nullptr;
-            PCR_CUDA(cudaMalloc(&tmp, sizeof(double) * (size_t)rows * k));
+            tmp = (double *)pool.raw_alloc(sizeof(double) * (size_t)rows * k);
             PCR_CUDA(cudaMemcpyAsync(tmp, h, sizeof(double) * (size_t)rows * k, cudaMemcpyHostToDevice, stream));
             k_pad_copy(ctx, tmp, rows, k, ld, dst);
             PCR_CUDA(cudaStreamSynchronize(stream));
-            cudaFree(tmp);
+            pool.raw_free(tmp);
         }
     }
     void get_matrix(const double *src, i64 rows, double *h) {
@@ -530,11 +536,11 @@ struct Engine {
             PCR_CUDA(cudaStreamSynchronize(stream));
         } else {
             double *tmp = nullptr;
-            PCR_CUDA(cudaMalloc(&tmp, sizeof(double) * (size_t)rows * k));
+            tmp = (double *)pool.raw_alloc(sizeof(double) * (size_t)rows * k);
             k_unpad_copy(ctx, src, rows, k, ld, tmp);
             PCR_CUDA(cudaMemcpyAsync(h, tmp, sizeof(double) * (size_t)rows * k, cudaMemcpyDeviceToHost, stream));
             PCR_CUDA(cudaStreamSynchronize(stream));
-            cudaFree(tmp);
+            pool.raw_free(tmp);
         }
     }
     void set_factors(const double *Uh, const double *Vh) {
@@ -1136,13 +1142,13 @@ int primalcr_level_counts(primalcr_engine *e, int32_t *cnt_left, int32_t *cnt_ri
     E->ensure_heavy_windows();
     const size_t n = (size_t)E->X.nnz * E->T;
     int32_t *dl = nullptr, *dr = nullptr;
-    PCR_CUDA(cudaMalloc(&dl, sizeof(int32_t) * (n ? n : 1)));
-    PCR_CUDA(cudaMalloc(&dr, sizeof(int32_t) * (n ? n : 1)));
+    dl = (int32_t *)E->pool.raw_alloc(sizeof(int32_t) * (n ? n : 1));
+    dr = (int32_t *)E->pool.raw_alloc(sizeof(int32_t) * (n ? n : 1));
     pcr::k_level_counts(E->ctx, E->X.row_ptr, E->d1, E->meta, E->T, dl, dr);
     E->sync();
     if (n && cnt_left) PCR_CUDA(cudaMemcpy(cnt_left, dl, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
     if (n && cnt_right) PCR_CUDA(cudaMemcpy(cnt_right, dr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
-    cudaFree(dl); cudaFree(dr);
+    E->pool.raw_free(dl); E->pool.raw_free(dr);
     API_END
 }
 

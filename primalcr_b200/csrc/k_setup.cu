@@ -85,34 +85,33 @@ void k_build_csc(Ctx &c, DevPool &pool, const int32_t *item, const int32_t *user
     if (nnz <= 0) return;
     // histogram -> exclusive scan = col_ptr
     unsigned long long *counts = nullptr;
-    PCR_CUDA(cudaMalloc(&counts, sizeof(unsigned long long) * (size_t)(d2 + 1)));
+    counts = (unsigned long long *)pool.raw_alloc(sizeof(unsigned long long) * (size_t)(d2 + 1));
     PCR_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)(d2 + 1), c.stream));
     LAUNCH(c, "csc_hist", 0.0, hist_kernel, grid_for(nnz, 256, c.sms * 16), 256, 0, item, nnz, counts);
     void *tmp = nullptr; size_t tb = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tb, (const i64 *)counts, col_ptr, (int)(d2 + 1), c.stream);
-    PCR_CUDA(cudaMalloc(&tmp, tb > 0 ? tb : 1));
+    tmp = pool.raw_alloc(tb > 0 ? tb : 1);
     c.prof->begin("csc_scan(cub)", c.stream, 0.0);
     PCR_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, (const i64 *)counts, col_ptr, (int)(d2 + 1), c.stream));
     c.prof->end(c.stream);
     PCR_CUDA(cudaStreamSynchronize(c.stream));
-    cudaFree(tmp); cudaFree(counts);
+    pool.raw_free(tmp); pool.raw_free(counts);
     // stable radix sort of (item -> CSR position): users stay ascending inside an item
     int32_t *keys_out = nullptr, *iota = nullptr;
-    PCR_CUDA(cudaMalloc(&keys_out, sizeof(int32_t) * (size_t)nnz));
-    PCR_CUDA(cudaMalloc(&iota, sizeof(int32_t) * (size_t)nnz));
+    keys_out = (int32_t *)pool.raw_alloc(sizeof(int32_t) * (size_t)nnz);
+    iota = (int32_t *)pool.raw_alloc(sizeof(int32_t) * (size_t)nnz);
     k_iota32(c, iota, nnz);
     int bits = 1;
     while (bits < 31 && ((i64)1 << bits) < d2) ++bits;
     tmp = nullptr; tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, item, keys_out, (const int32_t *)iota, csc2csr, nnz, 0, bits, c.stream);
-    PCR_CUDA(cudaMalloc(&tmp, tb > 0 ? tb : 1));
+    tmp = pool.raw_alloc(tb > 0 ? tb : 1);
     c.prof->begin("csc_sort(cub)", c.stream, 0.0);
     PCR_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, item, keys_out, (const int32_t *)iota, csc2csr, nnz, 0, bits, c.stream));
     c.prof->end(c.stream);
     LAUNCH(c, "csc_users", 0.0, gather_i32_kernel, grid_for(nnz, 256, c.sms * 16), 256, 0, user, csc2csr, nnz, csc_user);
     PCR_CUDA(cudaStreamSynchronize(c.stream));
-    cudaFree(tmp); cudaFree(keys_out); cudaFree(iota);
-    (void)pool;
+    pool.raw_free(tmp); pool.raw_free(keys_out); pool.raw_free(iota);
 }
 
 __global__ void csc_block_bounds_kernel(const i64 *__restrict__ col_ptr, const int32_t *__restrict__ csc_user, i64 d2, int nb,
@@ -140,6 +139,8 @@ void k_heavy_sort(Ctx &c, DevPool &pool, void **temp, size_t *temp_bytes, const 
     if (need > *temp_bytes) {
         *temp = pool.alloc<unsigned char>(need);      // grows monotonically; freed with the engine
         *temp_bytes = need;
+        // the pool allocates in the order of ITS stream; this sort may run on the side stream
+        if (pool.async && pool.stream != c.stream) PCR_CUDA(cudaStreamSynchronize(pool.stream));
     }
     c.prof->begin("heavy_sort(cub)", c.stream, 0.0);
     PCR_CUDA(cub::DeviceSegmentedSort::StableSortPairs(*temp, need, m, s_sorted, iota, pos_sorted, nnz, (i64)n_heavy,
