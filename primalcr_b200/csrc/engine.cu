@@ -139,7 +139,7 @@ struct Engine {
         PCR_CUDA(cudaMallocHost(&h_counters, sizeof(int) * 4));
         PCR_CUDA(cudaMallocHost(&h_stats, sizeof(i64) * 8));
         slots = pool.alloc<double>(32);
-        red_partials = pool.alloc<double>(1024);
+        red_partials = pool.alloc<double>(2048);     // >= 2 x RED_BLOCKS (k_cg_dots2 / k_cg_update)
         us.counters = pool.alloc<int>(4);
         ctx.ticket = pool.alloc<unsigned long long>(1);
         ctx_aux = ctx; ctx_aux.stream = aux;          // (the heavy-user kernels do not use the ticket counter)
@@ -722,18 +722,13 @@ struct Engine {
             coeffs(1, nullptr);
             rowsum_items(p, Hp);
             ++its;
-            k_dot(ctx, p, Hp, vn, red_partials, slots + 0);
-            k_dot(ctx, rr, p, vn, red_partials, slots + 1);
-            read_slots(2);
+            // p.Hp, rr.p -> alpha (on the device) -> delta, rr updated -> rr.rr, rr.Hp: two fused passes, ONE host read
+            k_cg_dots2(ctx, p, Hp, rr, vn, red_partials, slots + 0);
+            k_cg_update(ctx, delta, rr, p, Hp, vn, slots + 0, red_partials, slots + 2);
+            read_slots(4);
             const double prod_p_Hp = h_slots[0];
-            const double alpha = -1.0 * h_slots[1] / prod_p_Hp;
-            k_axpby(ctx, delta, 1.0, delta, alpha, p, vn);
-            k_axpby(ctx, rr, 1.0, rr, alpha, Hp, vn);
-            k_dot(ctx, rr, rr, vn, red_partials, slots + 0);
-            k_dot(ctx, rr, Hp, vn, red_partials, slots + 1);
-            read_slots(2);
-            if (std::sqrt(h_slots[0]) < err) break;
-            const double beta = h_slots[1] / prod_p_Hp;
+            if (std::sqrt(h_slots[2]) < err) break;
+            const double beta = h_slots[3] / prod_p_Hp;
             k_axpby(ctx, p, -1.0, rr, beta, p, vn);
         }
         // ---- line search: pcrpp.cpp:427-441

@@ -848,6 +848,61 @@ __global__ void __launch_bounds__(256) reduce_final_kernel(const double *__restr
     if (threadIdx.x == 0) *slot = t;
 }
 
+// ---- fused vector algebra of one V-side CG iteration (solve_delta_new pcrpp.cpp:344-352).  Same per-thread
+// accumulation order, block tree and final reduction as reduce_kernel<0>, so the scalars equal those of separate k_dot calls.
+// partials[0..RED_BLOCKS) <- p.Hp, partials[RED_BLOCKS..2 RED_BLOCKS) <- rr.p
+__global__ void __launch_bounds__(256) cg_dots2_kernel(const double *__restrict__ p, const double *__restrict__ Hp,
+                                                       const double *__restrict__ rr, i64 n, double *__restrict__ partials) {
+    __shared__ double wsum[8];
+    double a0 = 0.0, a1 = 0.0;
+    for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < n; i += (i64)gridDim.x * 256) {
+        const double pi = p[i];
+        a0 = fma(pi, Hp[i], a0);
+        a1 = fma(rr[i], pi, a1);
+    }
+    const double t0 = block_sum<256>(a0, wsum);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t0;
+    const double t1 = block_sum<256>(a1, wsum);
+    if (threadIdx.x == 0) partials[gridDim.x + blockIdx.x] = t1;
+}
+// alpha = -(rr.p) / (p.Hp) from slot[1], slot[0]; delta += alpha p; rr += alpha Hp; partials of rr.rr and rr.Hp
+__global__ void __launch_bounds__(256) cg_update_kernel(double *__restrict__ delta, double *__restrict__ rr,
+                                                        const double *__restrict__ p, const double *__restrict__ Hp, i64 n,
+                                                        const double *__restrict__ slot, double *__restrict__ partials) {
+    __shared__ double wsum[8];
+    const double alpha = -1.0 * slot[1] / slot[0];
+    double a0 = 0.0, a1 = 0.0;
+    for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < n; i += (i64)gridDim.x * 256) {
+        const double hp = Hp[i];
+        delta[i] = delta[i] + alpha * p[i];
+        const double r = rr[i] + alpha * hp;
+        rr[i] = r;
+        a0 = fma(r, r, a0);
+        a1 = fma(r, hp, a1);
+    }
+    const double t0 = block_sum<256>(a0, wsum);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t0;
+    const double t1 = block_sum<256>(a1, wsum);
+    if (threadIdx.x == 0) partials[gridDim.x + blockIdx.x] = t1;
+}
+// slot[b] = sum of partials[b * nb .. (b + 1) * nb)   (one block per slot)
+__global__ void __launch_bounds__(256) reduce_final_multi_kernel(const double *__restrict__ partials, int nb, double *__restrict__ slot) {
+    __shared__ double wsum[8];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nb; i += 256) acc += partials[(size_t)blockIdx.x * nb + i];
+    const double t = block_sum<256>(acc, wsum);
+    if (threadIdx.x == 0) slot[blockIdx.x] = t;
+}
+void k_cg_dots2(Ctx &c, const double *p, const double *Hp, const double *rr, i64 n, double *partials, double *slot2) {
+    LAUNCH(c, "cg_dots2", 24.0 * n, cg_dots2_kernel, RED_BLOCKS, 256, 0, p, Hp, rr, n, partials);
+    LAUNCH(c, "reduce_final", 0.0, reduce_final_multi_kernel, 2, 256, 0, partials, RED_BLOCKS, slot2);
+}
+void k_cg_update(Ctx &c, double *delta, double *rr, const double *p, const double *Hp, i64 n, const double *slot_in, double *partials,
+                 double *slot2_out) {
+    LAUNCH(c, "cg_update", 48.0 * n, cg_update_kernel, RED_BLOCKS, 256, 0, delta, rr, p, Hp, n, slot_in, partials);
+    LAUNCH(c, "reduce_final", 0.0, reduce_final_multi_kernel, 2, 256, 0, partials, RED_BLOCKS, slot2_out);
+}
+
 void k_fill(Ctx &c, double *x, i64 n, double v) {
     if (n <= 0) return;
     LAUNCH(c, "fill", 0.0, fill_kernel, grid_for(n, 1024, c.sms * 8), 256, 0, x, n, v);

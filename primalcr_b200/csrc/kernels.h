@@ -62,6 +62,12 @@ void k_fill_u8(Ctx &c, uint8_t *x, i64 n, uint8_t v);
 void k_axpby(Ctx &c, double *out, double a, const double *x, double b, const double *y, i64 n);  // out = a*x + b*y
 void k_dot(Ctx &c, const double *x, const double *y, i64 n, double *partials, double *slot);      // slot = x.y
 void k_sum(Ctx &c, const double *x, i64 n, double *partials, double *slot);
+// one V-side CG iteration's vector algebra in two passes (partials: >= 2 x 592 doubles):
+//   k_cg_dots2:  slot2[0] = p.Hp, slot2[1] = rr.p
+//   k_cg_update: alpha = -slot_in[1] / slot_in[0] (on the device); delta += alpha p; rr += alpha Hp; slot2_out = {rr.rr, rr.Hp}
+void k_cg_dots2(Ctx &c, const double *p, const double *Hp, const double *rr, i64 n, double *partials, double *slot2);
+void k_cg_update(Ctx &c, double *delta, double *rr, const double *p, const double *Hp, i64 n, const double *slot_in, double *partials,
+                 double *slot2_out);
 void k_sum_active(Ctx &c, const double *x, const uint8_t *mask, i64 n, double *partials, double *slot);
 void k_pad_copy(Ctx &c, const double *src, i64 rows, int k, int ld, double *dst);    // compact [rows x k] -> padded
 void k_unpad_copy(Ctx &c, const double *src, i64 rows, int k, int ld, double *dst);  // padded -> compact
