@@ -430,10 +430,11 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_LM_MINB : 1) tile_lm_sweep
     __shared__ double wagg[TH / 32];
     __shared__ int wflag[TH / 32];
     extern __shared__ __align__(16) unsigned char smraw[];
-    // dynamic layout: G[SLOTS] | sval[CAP] | G2[SLOTS] (objective only)
+    // dynamic layout: G[SLOTS] | sval[CAP] | G2[SLOTS] (objective) or stg[CAP] (coefficients: CSR-order staging of b / c)
     double *G = reinterpret_cast<double *>(smraw);
     double *sval = G + SLOTS;
     double *G2 = sval + CAP;
+    double *stg = sval + CAP;
     __shared__ double Kt[TILE_MAX_USERS * TT], Kt2[MODE == 2 ? TILE_MAX_USERS * TT : 1];
     __shared__ uint16_t Bt[TILE_MAX_USERS * (TT + 1)];
     const int tid = threadIdx.x;
@@ -461,8 +462,10 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_LM_MINB : 1) tile_lm_sweep
         }
     }
     if (MODE == 1) {
+        // b arrives in CSR order: read the tile's slice COALESCED and independently of the records (no dependent global
+        // gather), park it in shared memory and pick b[pos] from there
 #pragma unroll
-        for (int q = 0; q < TE; ++q) { const int i = tid + q * TH; if (i < ne) r_v[q] = b_g[e0 + (i64)(r_w0[q] & 0x1FFFull)]; }
+        for (int q = 0; q < TE; ++q) { const int i = tid + q * TH; if (i < ne) stg[i] = b_g[e0 + i]; }
     }
     if (!users_done) tile_users<TH>(ts, first_user, n_users, e0, row_ptr, active);
     // block starts of every user's levels (ranks inside the user)
@@ -474,9 +477,17 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_LM_MINB : 1) tile_lm_sweep
 #pragma unroll
     for (int q = 0; q < TE; ++q) {
         const int i = tid + q * TH;
-        if (i < ne) { ts.ul[i] = (uint8_t)((r_w0[q] >> 42) & 0x7Full); sval[i] = MODE == 2 ? r_v[q] - 1.0 : r_v[q]; }
+        if (i < ne) { ts.ul[i] = (uint8_t)((r_w0[q] >> 42) & 0x7Full); if (MODE != 1) sval[i] = MODE == 2 ? r_v[q] - 1.0 : r_v[q]; }
     }
     __syncthreads();
+    if (MODE == 1) {
+#pragma unroll
+        for (int q = 0; q < TE; ++q) {
+            const int i = tid + q * TH;
+            if (i < ne) { r_v[q] = stg[(int)(r_w0[q] & 0x1FFFull)]; sval[i] = r_v[q]; }
+        }
+        __syncthreads();
+    }
     tile_level_scan<double, 1, TH>(ts, ne, 1, G, wagg, wflag, [&](int i) { return sval[i]; }, [](int) { return 0; });
     if (MODE == 2)
         tile_level_scan<double, 1, TH>(ts, ne, 1, G2, wagg, wflag, [&](int i) { const double d = sval[i]; return d * d; }, [](int) { return 0; });
@@ -521,8 +532,15 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_LM_MINB : 1) tile_lm_sweep
         } else {
             const double lo = (double)(int)((w0 >> 13) & 0x1FFFull);
             const double cc = MODE == 0 ? lo * (v - 1.0) + hi * (v + 1.0) - acc : (lo + hi) * v - acc;
-            c_out[e0 + (i64)(w0 & 0x1FFFull)] = 2.0 * cc;
+            // unmasked launch: every position of the tile gets a value, so c goes back through shared memory and leaves
+            // as coalesced stores; masked launch (some users inactive): scattered stores of the active users only
+            if (active == nullptr) stg[(int)(w0 & 0x1FFFull)] = 2.0 * cc;
+            else c_out[e0 + (i64)(w0 & 0x1FFFull)] = 2.0 * cc;
         }
+    }
+    if (MODE != 2 && active == nullptr) {
+        __syncthreads();
+        for (int i = tid; i < ne; i += TH) c_out[e0 + i] = stg[i];
     }
     if (MODE == 2) {
         __syncthreads();
@@ -701,7 +719,7 @@ void k_tile_sweep(Ctx &c, int mode, const DevCsr &X, int geo, const uint8_t *act
     const unsigned grid = (unsigned)L.n;
     if (meta.lm_s != nullptr) {          // level-major fast path (scalar segmented scan)
 #define LM_ARGS L.first, L.nusers, L.e0, L.ne, active, X.row_ptr, X.user, meta, b, c_out, obj_user, T
-#define LM_LAUNCH(MODE, TT, TH, NAME) { const size_t sm = ((size_t)(TH * TE + TILE_MAX_USERS) * (MODE == 2 ? 2 : 1) + TH * TE) * 8; \
+#define LM_LAUNCH(MODE, TT, TH, NAME) { const size_t sm = ((size_t)(TH * TE + TILE_MAX_USERS) * (MODE == 2 ? 2 : 1) + TH * TE * (MODE == 2 ? 1 : 2)) * 8; \
         set_smem(tile_lm_sweep_kernel<MODE, TT, TH>, sm); LAUNCH(c, NAME, bytes, (tile_lm_sweep_kernel<MODE, TT, TH>), grid, TH, sm, LM_ARGS); }
 #define LM_MODE(MODE, NAME)                                                                                         \
         if (geo == 0) { if (T <= 5) { LM_LAUNCH(MODE, 5, 256, NAME) } else { LM_LAUNCH(MODE, 8, 256, NAME) } }        \
