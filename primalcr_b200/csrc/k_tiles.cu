@@ -699,7 +699,8 @@ void k_tile_prepare(Ctx &c, const DevCsr &X, int geo, const uint8_t *active, con
     const TileList &L = X.tiles[geo];
     if (L.n <= 0) return;
     PCR_REQUIRE(T <= 8, "tile kernels support at most 8 rating levels");
-    const double bytes = (double)L.nnz * (8 + 1 + 4 + 8 + 4 + 1 + 16);
+    // in: score 8 + user 4 + level 1; out: sorted score 8, position 4, level 1, ub/lb/cnt_lo/cnt_hi 16, level-major score 8 + records 16
+    const double bytes = (double)L.nnz * (13 + 29 + 24);
 #define PREP_ARGS L.first, L.nusers, L.e0, L.ne, active, X.row_ptr, X.user, m, X.level, meta.s, meta.pos, meta.lev, meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, T, meta
 #define PREP_LAUNCH(TT, TH, NAME) { const size_t sm = prepare_smem(T, TH * TE); set_smem(tile_prepare_kernel<TT, TH>, sm); \
         LAUNCH(c, NAME, bytes, (tile_prepare_kernel<TT, TH>), (unsigned)L.n, TH, sm, PREP_ARGS); }
@@ -714,7 +715,8 @@ void k_tile_sweep(Ctx &c, int mode, const DevCsr &X, int geo, const uint8_t *act
     const TileList &L = X.tiles[geo];
     if (L.n <= 0) return;
     PCR_REQUIRE(T <= 8, "tile kernels support at most 8 rating levels");
-    const double per = mode == 2 ? (8 + 1 + 4 + 4 + 4) : (mode == 1 ? (8 + 4 + 1 + 16 + 8 + 8) : (8 + 4 + 1 + 16 + 8));
+    // packed records 16 B + stream (score or b) 8 B + coefficient out 8 B (not for the objective)
+    const double per = mode == 2 ? (16 + 8) : (16 + 8 + 8);
     const double bytes = (double)L.nnz * per;
     const unsigned grid = (unsigned)L.n;
     if (meta.lm_s != nullptr) {          // level-major fast path (scalar segmented scan)
