@@ -387,11 +387,18 @@ def _custom_dataset(lens, d2, levels, seed):
     return Dataset(tr, Ratings.empty(d1, d2))
 
 
-@pytest.mark.parametrize("levels,k", [(7, 9), (2, 4), (8, 3), (12, 5)])
-def test_level_count_variants(levels, k):
-    """2, 7 and 8 rating levels go through the tile kernels (5- and 8-level instantiations), 12 levels through the
-    per-user kernels: one outer iteration against the oracle for each."""
-    ds = _custom_dataset([0, 3, 40, 1, 700, 129, 1500, 64, 2, 31], 2000, levels, seed=levels)
+@pytest.mark.parametrize("levels,k,heavy", [(7, 9, False), (2, 4, False), (8, 3, False), (12, 5, False),
+                                            (8, 4, True), (5, 6, True), (3, 5, True), (11, 3, True)])
+def test_level_count_variants(levels, k, heavy):
+    """2, 7 and 8 rating levels go through the tile kernels (5- and 8-level instantiations, two- and three-word packed
+    records), 12 levels through the per-user kernels: two outer iterations against the oracle for each.  heavy: adds a
+    2000-, a 4500- and a 9000-rating user (large tile / per-user class, and 3 / 5 chunks of the chunk-parallel path)."""
+    lens = [0, 3, 40, 1, 700, 129, 1500, 64, 2, 31]
+    d2 = 2000
+    if heavy:
+        lens = lens + [2000, 4500, 5, 9000, 17]
+        d2 = 12000
+    ds = _custom_dataset(lens, d2, levels, seed=levels)
     lam = 15.0
     e, U, V = make_engine(ds, k, lam, test=False)
     res = ob.oracle().train(2, to_csr(ds.train), None, U, V, lam, 2, do_predict=0)
