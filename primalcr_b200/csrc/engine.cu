@@ -842,7 +842,9 @@ struct Engine {
         DevCsr &C = which == 0 ? X : XT;
         PCR_REQUIRE(which == 0 || has_test, "no test set loaded");
         double *sc = which == 0 ? b : ev_score_t;
-        k_dots(ctx, U, C.user, V, C.item, C.nnz, ld, k, nullptr, sc, 0.0);
+        if (which == 0 && scores_valid) sc = m;                      // m already holds U_i . V_j of the current factors
+        else if (which == 0) train_dots(U, V, sc, nullptr);           // user-major units kernel (2x the generic one)
+        else k_dots(ctx, U, C.user, V, C.item, C.nnz, ld, k, nullptr, sc, 0.0);
         k_eval_pairs(ctx, C, sc, ev_err_item);
         k_eval_users(ctx, C, sc, ev_err_item, cfg.ndcg_k, ev_a, ev_b, ev_c, ev_d);
         k_sum(ctx, ev_a, C.d1, red_partials, slots + 0);
