@@ -152,8 +152,9 @@ struct DevCsr {
     i64 heavy_total = 0;         // sum over heavy users of (len + 1)
     i64 *heavy_begin = nullptr, *heavy_end = nullptr;  // [n_cls[2]] absolute segment bounds (CUB segmented sort)
     i64 max_len = 0;
-    // tiles of consecutive users: [0] small (<= TILE_CAP ratings in total), [1] large (users with TILE_CAP < len <= TILE_CAP_L)
-    TileList tiles[2];
+    // tiles of consecutive users: [0] small (<= TILE_CAP ratings in total), [1] medium (users with TILE_CAP < len <= TILE_CAP_M),
+    // [2] large (TILE_CAP_M < len <= TILE_CAP_L)
+    TileList tiles[3];
     // pair-tile work items (Primal-CR pair kernels and pairwise-error evaluation)
     int32_t *pt_user = nullptr; int32_t *pt_j0 = nullptr; i64 n_pt = 0;
     i64 *pt_ptr = nullptr;       // [d1+1] first work item of each user
@@ -204,6 +205,8 @@ struct HeavyLM {
 
 static const int TILE_CAP = 1024;        // ratings per tile of consecutive users (k_tiles.cu)
 static const int TILE_MAX_USERS = 128;   // users per tile
+static const int TILE_CAP_M = 2048;      // medium tiles: 512 threads, two CTAs per SM (most users above TILE_CAP are below 2048:
+                                         // in 4096-rating tiles they left 60 % of the threads idle)
 static const int TILE_CAP_L = 4096;      // large tiles: 1024 threads
 static const int S_CAP = 1024;   // block class  (256 threads, shared memory)
 static const int L_CAP = 4096;   // large class  (1024 threads, shared memory)

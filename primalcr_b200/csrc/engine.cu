@@ -286,24 +286,26 @@ struct Engine {
         i64 htot = 0;
         use_tiles = (T <= 8) && (getenv("PRIMALCR_NO_TILES") == nullptr);
         // tiles: runs of consecutive users; geometry 0 takes users with len <= TILE_CAP, geometry 1 users with
-        // TILE_CAP < len <= TILE_CAP_L; anything longer goes to the per-user heavy class
+        // TILE_CAP < len <= TILE_CAP_M, geometry 2 users with TILE_CAP_M < len <= TILE_CAP_L; anything longer is heavy
         struct Builder { std::vector<int32_t> first, num; i64 cur_first = -1, cur_nnz = 0, cur_users = 0, nnz = 0; i64 cap;
             void close() { if (cur_first >= 0 && cur_nnz > 0) { first.push_back((int32_t)cur_first); num.push_back((int32_t)cur_users); nnz += cur_nnz; }
                            cur_first = -1; cur_nnz = 0; cur_users = 0; }
             void add(i64 u, i64 len) { if (cur_first >= 0 && (cur_nnz + len > cap || cur_users + 1 > TILE_MAX_USERS)) close();
                                        if (cur_first < 0) cur_first = u; cur_nnz += len; cur_users += 1; } };
-        Builder tb[2]; tb[0].cap = TILE_CAP; tb[1].cap = TILE_CAP_L;
+        Builder tb[3]; tb[0].cap = TILE_CAP; tb[1].cap = TILE_CAP_M; tb[2].cap = TILE_CAP_L;
+        const bool one_geometry = getenv("PRIMALCR_NO_TILE_M") != nullptr;     // A/B: medium users in the large tiles
         for (i64 u = 0; u < d1; ++u) {
             const i64 len = X.h_row_ptr[u + 1] - X.h_row_ptr[u];
-            if (use_tiles && len <= TILE_CAP) { tb[1].close(); tb[0].add(u, len); continue; }
-            if (use_tiles && T <= 5 && len <= TILE_CAP_L) { tb[0].close(); tb[1].add(u, len); continue; }   // T>5: smem
-            tb[0].close(); tb[1].close();
+            if (use_tiles && len <= TILE_CAP) { tb[1].close(); tb[2].close(); tb[0].add(u, len); continue; }
+            if (use_tiles && T <= 5 && len <= TILE_CAP_M && !one_geometry) { tb[0].close(); tb[2].close(); tb[1].add(u, len); continue; }   // T>5: smem
+            if (use_tiles && T <= 5 && len <= TILE_CAP_L) { tb[0].close(); tb[1].close(); tb[2].add(u, len); continue; }
+            tb[0].close(); tb[1].close(); tb[2].close();
             if (len == 0) continue;
             if (len <= S_CAP) cls[0].push_back((int32_t)u);
             else if (len <= L_CAP) cls[1].push_back((int32_t)u);
             else { cls[2].push_back((int32_t)u); hoff[u] = htot; htot += len + 1; hb.push_back(X.h_row_ptr[u]); he.push_back(X.h_row_ptr[u + 1]); }
         }
-        for (int gq = 0; gq < 2; ++gq) {
+        for (int gq = 0; gq < 3; ++gq) {
             tb[gq].close();
             X.tiles[gq].n = (i64)tb[gq].first.size(); X.tiles[gq].nnz = tb[gq].nnz;
             X.tiles[gq].first = upload_vec(tb[gq].first); X.tiles[gq].nusers = upload_vec(tb[gq].num);
@@ -598,7 +600,7 @@ struct Engine {
             k_gather_level(hc, X.cls_users[2], X.n_cls[2], nullptr, X.row_ptr, X.level, meta);
             if (heavy_chunked) k_heavy_prepare(hc, hv, meta, T);
         }
-        for (int gq = 0; gq < 2; ++gq) k_tile_prepare(ctx, X, gq, active, sc, meta, T);
+        for (int gq = 0; gq < 3; ++gq) k_tile_prepare(ctx, X, gq, active, sc, meta, T);
         k_sort_users(ctx, 0, X.cls_users[0], X.n_cls[0], active, X.row_ptr, sc, X.level, meta);
         k_sort_users(ctx, 1, X.cls_users[1], X.n_cls[1], active, X.row_ptr, sc, X.level, meta);
         for (int q = 0; q < 3; ++q) {
@@ -612,7 +614,7 @@ struct Engine {
     void sweep_coeff(int mode, const uint8_t *active, const double *bsrc) {
         const bool par = heavy_on_aux();
         if (par) { fork_aux(); k_heavy_sweep(ctx_aux, mode, hv, active, meta, bsrc, cbuf, nullptr, T); }
-        for (int gq = 0; gq < 2; ++gq) k_tile_sweep(ctx, mode, X, gq, active, meta, bsrc, cbuf, nullptr, T);
+        for (int gq = 0; gq < 3; ++gq) k_tile_sweep(ctx, mode, X, gq, active, meta, bsrc, cbuf, nullptr, T);
         if (par) join_aux();
         for (int q = 0; q < 3; ++q) {
             if (q == 2 && heavy_chunked) { if (!par) k_heavy_sweep(ctx, mode, hv, active, meta, bsrc, cbuf, nullptr, T); continue; }
@@ -622,7 +624,7 @@ struct Engine {
     void sweep_obj(const uint8_t *active) {
         const bool par = heavy_on_aux();
         if (par) { fork_aux(); k_heavy_sweep(ctx_aux, 2, hv, active, meta, nullptr, nullptr, us.loss, T); }
-        for (int gq = 0; gq < 2; ++gq) k_tile_sweep(ctx, 2, X, gq, active, meta, nullptr, nullptr, us.loss, T);
+        for (int gq = 0; gq < 3; ++gq) k_tile_sweep(ctx, 2, X, gq, active, meta, nullptr, nullptr, us.loss, T);
         if (par) join_aux();
         for (int q = 0; q < 3; ++q) {
             if (q == 2 && heavy_chunked) { if (!par) k_heavy_sweep(ctx, 2, hv, active, meta, nullptr, nullptr, us.loss, T); continue; }

@@ -152,7 +152,7 @@ __device__ __forceinline__ bool tile_users(TileShared<TH * TE> &ts, int first_us
 #define PCR_PREP_MINB 4
 #endif
 template <int TT, int TH>
-__global__ void __launch_bounds__(TH, TH == 256 ? PCR_PREP_MINB : 1) tile_prepare_kernel(const int32_t *__restrict__ tile_first,
+__global__ void __launch_bounds__(TH, TH == 256 ? PCR_PREP_MINB : (TH == 512 ? 2 : 1)) tile_prepare_kernel(const int32_t *__restrict__ tile_first,
                                                           const int32_t *__restrict__ tile_nusers,
                                                           const i64 *__restrict__ tile_e0, const int32_t *__restrict__ tile_ne,
                                                           const uint8_t *__restrict__ active,
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_PREP_MINB : 1) tile_prepar
 #define PCR_LM_MINB 5      // measured with the packed records: 4 -> 21.2, 5 -> 18.5, 6 -> 19.8 ms per iteration (Hv sweeps)
 #endif
 template <int MODE, int TT, int TH>
-__global__ void __launch_bounds__(TH, TH == 256 ? PCR_LM_MINB : 1) tile_lm_sweep_kernel(const int32_t *__restrict__ tile_first,
+__global__ void __launch_bounds__(TH, TH == 256 ? PCR_LM_MINB : (TH == 512 ? 2 : 1)) tile_lm_sweep_kernel(const int32_t *__restrict__ tile_first,
                                                            const int32_t *__restrict__ tile_nusers,
                                                            const i64 *__restrict__ tile_e0, const int32_t *__restrict__ tile_ne,
                                                            const uint8_t *__restrict__ active,
@@ -694,7 +694,7 @@ static void set_smem(K kernel, size_t bytes) {
     PCR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
-// geo 0: small tiles (256 threads x 4 = TILE_CAP ratings), geo 1: large tiles (1024 threads x 4 = TILE_CAP_L ratings)
+// geo 0: small tiles (256 threads x 4 = TILE_CAP ratings), geo 1: medium (512 threads, TILE_CAP_M), geo 2: large (1024 threads, TILE_CAP_L)
 void k_tile_prepare(Ctx &c, const DevCsr &X, int geo, const uint8_t *active, const double *m, SortedMeta &meta, int T) {
     const TileList &L = X.tiles[geo];
     if (L.n <= 0) return;
@@ -704,8 +704,9 @@ void k_tile_prepare(Ctx &c, const DevCsr &X, int geo, const uint8_t *active, con
 #define PREP_ARGS L.first, L.nusers, L.e0, L.ne, active, X.row_ptr, X.user, m, X.level, meta.s, meta.pos, meta.lev, meta.ub, meta.lb, meta.cnt_lo, meta.cnt_hi, T, meta
 #define PREP_LAUNCH(TT, TH, NAME) { const size_t sm = prepare_smem(T, TH * TE); set_smem(tile_prepare_kernel<TT, TH>, sm); \
         LAUNCH(c, NAME, bytes, (tile_prepare_kernel<TT, TH>), (unsigned)L.n, TH, sm, PREP_ARGS); }
-    if (geo == 0) { if (T <= 5) PREP_LAUNCH(5, 256, "tile_prepare") else PREP_LAUNCH(8, 256, "tile_prepare") }
-    else          { if (T <= 5) PREP_LAUNCH(5, 1024, "tile_prepare_L") else PREP_LAUNCH(8, 1024, "tile_prepare_L") }
+    if (geo == 0)      { if (T <= 5) PREP_LAUNCH(5, 256, "tile_prepare") else PREP_LAUNCH(8, 256, "tile_prepare") }
+    else if (geo == 1) { PCR_REQUIRE(T <= 5, "medium tiles need T <= 5"); PREP_LAUNCH(5, 512, "tile_prepare_M") }
+    else               { PCR_REQUIRE(T <= 5, "large tiles need T <= 5"); PREP_LAUNCH(5, 1024, "tile_prepare_L") }
 #undef PREP_LAUNCH
 #undef PREP_ARGS
 }
@@ -724,8 +725,9 @@ void k_tile_sweep(Ctx &c, int mode, const DevCsr &X, int geo, const uint8_t *act
 #define LM_LAUNCH(MODE, TT, TH, NAME) { const size_t sm = ((size_t)(TH * TE + TILE_MAX_USERS) * (MODE == 2 ? 2 : 1) + TH * TE * (MODE == 2 ? 1 : 2)) * 8; \
         set_smem(tile_lm_sweep_kernel<MODE, TT, TH>, sm); LAUNCH(c, NAME, bytes, (tile_lm_sweep_kernel<MODE, TT, TH>), grid, TH, sm, LM_ARGS); }
 #define LM_MODE(MODE, NAME)                                                                                         \
-        if (geo == 0) { if (T <= 5) { LM_LAUNCH(MODE, 5, 256, NAME) } else { LM_LAUNCH(MODE, 8, 256, NAME) } }        \
-        else          { LM_LAUNCH(MODE, 5, 1024, NAME "_L") }
+        if (geo == 0)      { if (T <= 5) { LM_LAUNCH(MODE, 5, 256, NAME) } else { LM_LAUNCH(MODE, 8, 256, NAME) } }   \
+        else if (geo == 1) { LM_LAUNCH(MODE, 5, 512, NAME "_M") }                                                    \
+        else               { LM_LAUNCH(MODE, 5, 1024, NAME "_L") }
         if (mode == 0) { LM_MODE(0, "lm_sweep_grad") }
         else if (mode == 1) { LM_MODE(1, "lm_sweep_hv") }
         else { LM_MODE(2, "lm_sweep_obj") }
@@ -738,8 +740,9 @@ void k_tile_sweep(Ctx &c, int mode, const DevCsr &X, int geo, const uint8_t *act
 #define SW_LAUNCH(MODE, TT, TH, NAME) { const size_t sm = sweep_smem(T, TH * TE); set_smem(tile_sweep_kernel<MODE, TT, TH>, sm); \
         LAUNCH(c, NAME, bytes, (tile_sweep_kernel<MODE, TT, TH>), grid, TH, sm, SW_ARGS); }
 #define SW_MODE(MODE, NAME)                                                                                         \
-    if (geo == 0) { if (T <= 5) SW_LAUNCH(MODE, 5, 256, NAME) else SW_LAUNCH(MODE, 8, 256, NAME) }                   \
-    else          { if (T <= 5) SW_LAUNCH(MODE, 5, 1024, NAME "_L") else SW_LAUNCH(MODE, 8, 1024, NAME "_L") }
+    if (geo == 0)      { if (T <= 5) SW_LAUNCH(MODE, 5, 256, NAME) else SW_LAUNCH(MODE, 8, 256, NAME) }              \
+    else if (geo == 1) { SW_LAUNCH(MODE, 5, 512, NAME "_M") }                                                        \
+    else               { SW_LAUNCH(MODE, 5, 1024, NAME "_L") }
     if (mode == 0) { SW_MODE(0, "tile_sweep_grad") }
     else if (mode == 1) { SW_MODE(1, "tile_sweep_hv") }
     else { SW_MODE(2, "tile_sweep_obj") }

@@ -89,7 +89,7 @@ void k_u_commit(Ctx &c, UState &s, double *U, i64 d1, int ld);
 void k_u_stats(Ctx &c, UState &s, const i64 *row_ptr, i64 d1, i64 *out8 /* device, 8 slots */);
 
 // ---------------------------------------------------------------- k_tiles.cu (tiles of consecutive small users)
-// geo 0: small tiles (users <= TILE_CAP ratings), geo 1: large tiles (TILE_CAP < len <= TILE_CAP_L)
+// geo 0: small tiles (users <= TILE_CAP ratings), geo 1: medium (TILE_CAP < len <= TILE_CAP_M), geo 2: large (<= TILE_CAP_L)
 void k_tile_prepare(Ctx &c, const DevCsr &X, int geo, const uint8_t *active, const double *m, SortedMeta &meta, int T);
 // mode 0 gradient coefficient, 1 Hv coefficient (stream b), 2 per-user loss
 void k_tile_sweep(Ctx &c, int mode, const DevCsr &X, int geo, const uint8_t *active, const SortedMeta &meta, const double *b,
