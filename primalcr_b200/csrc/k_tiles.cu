@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_PREP_MINB : (TH == 512 ? 2
 #pragma unroll
                 for (int q = 0; q < TE; ++q) {
                     const unsigned long long o = pk[pp + q];
-                    ek[q] = keep_min ? (o < ek[q] ? o : ek[q]) : (o > ek[q] ? o : ek[q]);
+                    ek[q] = ((o < ek[q]) == keep_min) ? o : ek[q];      // one 64-bit compare (equal keys only among the padding)
                 }
             }
             if (live) {
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(TH, TH == 256 ? PCR_PREP_MINB : (TH == 512 ? 2
 #pragma unroll
                     for (int q = 0; q < TE; ++q) {
                         const unsigned long long o = __shfl_xor_sync(FULL, ek[q], m);
-                        ek[q] = keep_min ? (o < ek[q] ? o : ek[q]) : (o > ek[q] ? o : ek[q]);
+                        ek[q] = ((o < ek[q]) == keep_min) ? o : ek[q];      // one 64-bit compare (equal keys only among the padding)
                     }
                 }
                 if (k >= 4) {                                   // j = 2: pairs (0,2), (1,3); direction is per thread for k >= 4
