@@ -210,7 +210,10 @@ static const int TILE_CAP_M = 2048;      // medium tiles: 512 threads, two CTAs 
 static const int TILE_CAP_L = 4096;      // large tiles: 1024 threads
 static const int S_CAP = 1024;   // block class  (256 threads, shared memory)
 static const int L_CAP = 4096;   // large class  (1024 threads, shared memory)
-static const int ROWSUM_CHUNK = 256;
+#ifndef PCR_ROWSUM_CHUNK
+#define PCR_ROWSUM_CHUNK 256
+#endif
+static const int ROWSUM_CHUNK = PCR_ROWSUM_CHUNK;
 static const int PAIR_TJ = 256;  // j elements per pair work item
 static const int MAX_LEVELS = 32;
 
