@@ -32,7 +32,7 @@ def main():
     if ph:
         out.append("| e2e phases (s): engine create / set_train (upload + CSC + work lists) / set_factors / run (initial objective + %d iterations) / get_factors | %s |" % (d["steps"], " / ".join("%.3f" % ph[k_] for k_ in ("create", "set_train", "set_factors", "run", "get_factors"))))
     out.append("| kernels launched per timed iteration (`gpu_launches` / steps) | %d |" % (d["gpu_launches"] // d["steps"]))
-    out.append("\n`B_alg / t` exceeds the HBM peak because the logical k-vector touches counted by `B_alg` are mostly served on chip:\nV (14 MB) is L2-resident for the user-major gathers, and the item-major row-sum walks U in 24 MB user blocks, so its\ngathered rows hit L2 as well.  `roofline.traffic` (ncu DRAM bytes per launch, `r01_traffic.json`) shows the real HBM\ntraffic: 9.0 GB per item-major row-sum launch against 81.2 GB algorithmic, 1.6 GB per `dots` launch.\nThe timed iterations (4-6 from the N(0,1) init) run 7.1 len-weighted U-side CG rounds; `tools/ab.py` (iterations 3-4, 5.8\nrounds, no per-launch events) reads 0.2335 s for the same build.\n")
+    out.append("\n`B_alg / t` exceeds the HBM peak because the logical k-vector touches counted by `B_alg` are mostly served on chip:\nV (14 MB) is L2-resident for the user-major gathers, and the item-major row-sum walks U in 24 MB user blocks, so its\ngathered rows hit L2 as well.  `roofline.traffic` (ncu DRAM bytes per launch, `r01_traffic.json`) shows the real HBM\ntraffic: 9.0 GB per item-major row-sum launch against 81.2 GB algorithmic, 1.6 GB per `dots` launch.\nThe timed iterations (4-6 from the N(0,1) init) run 7.1 len-weighted U-side CG rounds; `tools/ab.py` (iterations 3-4, 5.8\nrounds, no per-launch events) reads 0.229 s for the same build.\n")
     out.append("## Per-kernel table (CUDA events inside the timed region)\n")
     out.append("| kernel | ms/step | launches/step | algorithmic GB/s |\n|---|---|---|---|")
     for k in d["roofline"]["kernels"]:
@@ -40,17 +40,17 @@ def main():
     out.append("")
     if os.path.exists(P("r01_ncu_full_size_summary.txt")):
         out.append("## ncu `--set full` at FULL size (one outer iteration; `.ncu-rep` not committed, 60 MB)\n")
-        out.append("Commands (each after `python tools/profile_step.py --scale 1.0` had exited 0 without ncu): `ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:\"rowsum_kernel|dots_units_kernel|tile_lm_sweep_kernel\" -s 3 -c 4 python tools/profile_step.py --scale 1.0`; the same with `-k regex:\"tile_prepare_kernel\" -c 2` and `-k regex:\"hv_chunk|hv_lookup|rowsum_finalize|u_cg_step\" -s 3 -c 6`.\n")
+        out.append("Commands (each after `python tools/profile_step.py --scale 1.0` had exited 0 without ncu): `ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:\"rowsum_kernel|dots_units_kernel|tile_lm_sweep_kernel\" -s 4 -c 5 python tools/profile_step.py --scale 1.0`; the same with `-k regex:\"tile_prepare_kernel\" -c 3` and `-k regex:\"hv_chunk|hv_lookup|rowsum_finalize|u_cg_step\" -s 3 -c 6`.\n")
         out.append("```\n" + open(P("r01_ncu_full_size_summary.txt")).read().strip() + "\n```\n")
-        out.append("Reading:\n* `dots_units_kernel<8,7>` (81.2 GB algorithmic per launch, 4.18 ms = 19.4 TB/s): 1.6 GB of DRAM traffic, L2 hit 97 %, l1tex throughput 85 %, L2 throughput 75 % (busiest slice 92 %) -> bound by the L2 -> SM data path and load latency at a full register file, not by HBM.  Fewer shuffles, L1 / L2 cache-policy hints, a shared-memory copy of the hottest rows and 256-bit loads were all measured and changed nothing or lost (profiles/experiments/README.md).\n* `rowsum_kernel<2>` item-major (81.2 GB algorithmic, 5.82 ms = 14 TB/s): 9.0 GB DRAM (U once + the 8-byte coefficient gather through csc2csr + indices + partial sums), L2 hit 83 %, stall reason `long_scoreboard`.\n* `tile_lm_sweep_kernel<1,5,256>` (Hv sweep, 32 B/rating with the packed records): 2.7 GB DRAM in 1.13 ms = 2.4 TB/s, 5 CTAs/SM (48 registers), issue 56 %: latency of the load phase + scalar segmented scan.\n* `tile_prepare_kernel<5,256>`: issue slots 74 % busy -- instruction-bound (64-bit compare-exchange network in registers / shuffles, window binary searches, 5-level count scan); DRAM 5.5 GB per launch (writes dominate: sorted outputs + level-major records).\n* heavy users (`hv_*`, 621 chunks of 2048 ratings): sums 10 us + scan 20 us + look-ups 42 us per sweep on the high-priority side stream, against 144 us for the one-CTA-per-user kernel they replace.\n")
+        out.append("Reading:\n* `dots_units_kernel<8,7>` (81.2 GB algorithmic per launch, 4.18 ms = 19.4 TB/s): 1.6 GB of DRAM traffic, L2 hit 97 %, l1tex throughput 85 %, L2 throughput 75 % (busiest slice 92 %) -> bound by the L2 -> SM data path and load latency at a full register file, not by HBM.  Fewer shuffles, L1 / L2 cache-policy hints, a shared-memory copy of the hottest rows and 256-bit loads were all measured and changed nothing or lost (profiles/experiments/README.md).\n* `rowsum_kernel<2>` item-major (81.2 GB algorithmic, 5.82 ms = 14 TB/s): 9.0 GB DRAM (U once + the 8-byte coefficient gather through csc2csr + indices + partial sums), L2 hit 83 %, stall reason `long_scoreboard`.\n* `tile_lm_sweep_kernel<1,5,256>` (Hv sweep, 32 B/rating with the packed records): 2.7 GB DRAM in 1.12 ms = 2.4 TB/s, 5 CTAs/SM (48 registers), issue 56 %: latency of the load phase + scalar segmented scan.  `<1,5,512>` / `<1,5,1024>` are the medium (1024 < len <= 2048, two CTAs/SM) and large (<= 4096) tile geometries: 0.21 + 0.09 ms, against 0.47 ms when both shared the 4096-rating tiles (39 % full).\n* `tile_prepare_kernel<5,256>` (4.45 ms; 4.93 before the single-compare exchange): issue slots ~74 % busy -- instruction-bound (64-bit compare-exchange network in registers / shuffles, window binary searches, 5-level count scan); DRAM 5.5 GB per launch (writes dominate: sorted outputs + level-major records).\n* heavy users (`hv_*`, 621 chunks of 2048 ratings): sums 10 us + scan 20 us + look-ups 42 us per sweep on the high-priority side stream, against 144 us for the one-CTA-per-user kernel they replace.\n")
     out.append("## Launch lists (`--metrics gpu__time_duration.sum --clock-control none`)\n")
-    out.append("* `r01_ncu_launches_bench_netflix_k100.csv` — the bench command itself (`python bench.py --steps 1 --warmup 3 --no-cpu-baseline`, full size; the list also holds torch's data-generation kernels, which run before the timed region). Shares over all `pcr::` launches vs the CUDA-event table above: rowsum_kernel 39.8 % (events: 41.2 %), dots_units 31.9 % (32.8 %), lm_sweep Hv 11.5 % (12.6 %), tile_prepare 7.5 % (6.1 %): the kernel shares agree.\n* `r01_ncu_launches_netflix0.2_k100.csv`, `r01_ncu_top_kernels_v1.md` — the FIRST correct path (v1, 0.652 s/iter) at scale 0.2, kept to show where the optimisation started (sweep: 37 warp-instructions per rating; grids sized past occupancy).\n* `experiments/` — measured-and-rejected variants (patches + result tables).\n")
+    out.append("* `r01_ncu_launches_bench_netflix_k100.csv` — the bench command itself (`python bench.py --steps 1 --warmup 3 --no-cpu-baseline`, full size; the list also holds torch's data-generation kernels, which run before the timed region). Shares over all `pcr::` launches vs the CUDA-event table above: rowsum_kernel 41.0 % (events: 42.3 %), dots_units 33.0 % (33.9 %), lm_sweep Hv 10.5 % (11.5 %), tile_prepare 6.3 % (5.2 %): the kernel shares agree.\n* `r01_ncu_launches_netflix0.2_k100.csv`, `r01_ncu_top_kernels_v1.md` — the FIRST correct path (v1, 0.652 s/iter) at scale 0.2, kept to show where the optimisation started (sweep: 37 warp-instructions per rating; grids sized past occupancy).\n* `experiments/` — measured-and-rejected variants (patches + result tables).\n")
     out.append("## Multi-GPU (strong scaling, same data set, users sharded by nnz; `r01_bench_netflix_k100_{2,4,8}gpu.json`)\n")
     out.append("| GPUs | s / outer iteration | parallel efficiency t1/(n tn) | e2e s / iteration | objective after 6 iterations |\n|---|---|---|---|---|")
     out.append("| 1 | %.4f | 1.00 | %.3f | %.15g |" % (d["value"], d["e2e"]["value"], d["objective"][-1]))
     for n, s in sorted(scal.items()):
         out.append("| %d | %.4f | %.2f | %.3f | %.15g |" % (n, s["value"], d["value"] / (n * s["value"]), s["e2e"]["value"], s["objective"][-1]))
-    out.append("\nEvery rank's kernel totals are in the `per_rank` key of the N > 1 files (user shards balanced by nnz: all kernels within 0.5 %\nacross ranks at N = 8).  e2e at N > 1 re-attaches to the process's cached NCCL communicator and allocates from the\nstream-ordered pool (plain cudaMalloc is ~10x slower once NCCL has enabled peer access: 0.50 -> 0.13 s/iter at N = 2).\n")
+    out.append("\nEvery rank's kernel totals are in the `per_rank` key of the N > 1 files (user shards balanced by nnz: all kernels within 0.5 %\nacross ranks at N = 8).  e2e at N > 1 re-attaches to the process's cached NCCL communicator and allocates from the\nstream-ordered pool (plain cudaMalloc is ~10x slower once NCCL has enabled peer access: 0.50 -> 0.13 s/iter at N = 2).\nThe N = 2/4/8 files predate the pitched factor download: the N = 4 e2e still holds 0.30 s of `get_factors` (its staging\nbuffer made the pool grow; at N = 1 the same fix took get_factors from 0.097 to 0.008 s).\n")
     for fn, title in (("r01_other_shapes_1gpu.jsonl", "Other BASELINE.json shapes, scaled, 1 GPU"),
                       ("r01_other_shapes_full_size_1gpu.jsonl", "Yahoo-shape and power-law shape at FULL size, 1 GPU")):
         if not os.path.exists(P(fn)):
