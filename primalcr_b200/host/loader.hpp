@@ -10,6 +10,7 @@
 // grouped by user like convert(testset_t&) requires (util.cpp:257-266).
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -51,27 +52,45 @@ inline void parse_chunk(const char *p, const char *end, Triples &out) {
         while (p < end && *p >= '0' && *p <= '9') b = b * 10 + (*p++ - '0');
         if (neg) b = -b;
         while (p < end && (*p == ' ' || *p == '\t')) ++p;
-        // rating: fast path for plain decimals, strtod for anything else (exponents, inf, ...)
+        // rating: plain decimals "[-]ddd[.ddd]" with <= 15 significant digits are converted exactly (integer mantissa
+        // divided by an exactly representable power of ten = the correctly rounded value, i.e. what strtod / sscanf
+        // "%lf" return); anything else (exponents, inf, nan, long mantissas) goes through strtod
         const char *q = p;
-        while (q < end && *q != '\n') ++q;
-        char buf[64];
-        size_t len = (size_t)(q - p);
-        if (len > 63) len = 63;
-        memcpy(buf, p, len); buf[len] = 0;
-        const double v = strtod(buf, nullptr);
+        bool rneg = false;
+        if (q < end && (*q == '-' || *q == '+')) { rneg = *q == '-'; ++q; }
+        unsigned long long mant = 0; int nd = 0, frac = 0;
+        while (q < end && *q >= '0' && *q <= '9') { mant = mant * 10 + (unsigned)(*q++ - '0'); ++nd; }
+        if (q < end && *q == '.') { ++q; while (q < end && *q >= '0' && *q <= '9') { mant = mant * 10 + (unsigned)(*q++ - '0'); ++nd; ++frac; } }
+        const bool at_end = q >= end || *q == '\n' || *q == '\r' || *q == ' ' || *q == '\t';
+        double v;
+        if (nd > 0 && nd <= 15 && at_end) {
+            static const double p10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+            v = (double)mant / p10[frac];
+            if (rneg) v = -v;
+            while (q < end && *q != '\n') ++q;
+        } else {
+            q = p;
+            while (q < end && *q != '\n') ++q;
+            char buf[64];
+            size_t len = (size_t)(q - p);
+            if (len > 63) len = 63;
+            memcpy(buf, p, len); buf[len] = 0;
+            v = strtod(buf, nullptr);
+        }
         out.u.push_back((int32_t)(a - 1)); out.i.push_back((int32_t)(b - 1)); out.r.push_back(v);
         p = q;
     }
 }
 
-// parses at most `limit` entries (the reference reads exactly the count given in meta)
-inline Triples parse_file(const std::string &path, int64_t limit) {
+// parses at most `limit` entries (the reference reads exactly the count given in meta); the result stays split into the
+// per-thread parts, in file order
+inline std::vector<Triples> parse_file_parts(const std::string &path, int64_t limit) {
     int fd = open(path.c_str(), O_RDONLY);
     if (fd < 0) throw std::runtime_error("cannot open " + path);
     struct stat st; fstat(fd, &st);
     const size_t size = (size_t)st.st_size;
-    Triples all;
-    if (size == 0) { close(fd); return all; }
+    std::vector<Triples> part;
+    if (size == 0) { close(fd); return part; }
     const char *base = (const char *)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
     if (base == MAP_FAILED) { close(fd); throw std::runtime_error("mmap failed for " + path); }
     int nt = 1;
@@ -86,41 +105,84 @@ inline Triples parse_file(const std::string &path, int64_t limit) {
         while (c < size && base[c] != '\n') ++c;
         cut[t] = c < size ? c + 1 : size;
     }
-    std::vector<Triples> part(nt);
+    part.resize(nt);
 #pragma omp parallel for schedule(static, 1)
     for (int t = 0; t < nt; ++t) {
-        part[t].u.reserve((cut[t + 1] - cut[t]) / 12 + 16);
+        const size_t guess = (cut[t + 1] - cut[t]) / 12 + 16;
+        part[t].u.reserve(guess); part[t].i.reserve(guess); part[t].r.reserve(guess);
         parse_chunk(base + cut[t], base + cut[t + 1], part[t]);
     }
     munmap((void *)base, size); close(fd);
+    if (limit >= 0) {                       // keep the first `limit` entries of the file
+        int64_t left = limit;
+        for (auto &p : part) {
+            const int64_t n = std::min<int64_t>((int64_t)p.u.size(), left);
+            p.u.resize((size_t)n); p.i.resize((size_t)n); p.r.resize((size_t)n);
+            left -= n;
+        }
+    }
+    return part;
+}
+
+inline Triples concat_parts(const std::vector<Triples> &part) {
+    Triples all;
     size_t total = 0;
     for (auto &p : part) total += p.u.size();
-    if (limit >= 0 && (size_t)limit < total) total = (size_t)limit;
     all.u.resize(total); all.i.resize(total); all.r.resize(total);
-    size_t off = 0;
-    for (auto &p : part) {
-        const size_t n = std::min(p.u.size(), total - off);
-        std::copy(p.u.begin(), p.u.begin() + n, all.u.begin() + off);
-        std::copy(p.i.begin(), p.i.begin() + n, all.i.begin() + off);
-        std::copy(p.r.begin(), p.r.begin() + n, all.r.begin() + off);
-        off += n;
-        if (off >= total) break;
+    std::vector<size_t> off(part.size() + 1, 0);
+    for (size_t t = 0; t < part.size(); ++t) off[t + 1] = off[t] + part[t].u.size();
+#pragma omp parallel for schedule(static, 1)
+    for (int64_t t = 0; t < (int64_t)part.size(); ++t) {
+        std::copy(part[t].u.begin(), part[t].u.end(), all.u.begin() + off[t]);
+        std::copy(part[t].i.begin(), part[t].i.end(), all.i.begin() + off[t]);
+        std::copy(part[t].r.begin(), part[t].r.end(), all.r.begin() + off[t]);
     }
     return all;
 }
 
-// CSR sorted by (user, item): the order of smat_t::load_from_iterator util.h:240-247
-inline Csr build_train_csr(int64_t d1, int64_t d2, const Triples &t) {
-    Csr X; X.d1 = d1; X.d2 = d2; X.nnz = (int64_t)t.u.size();
+inline Triples parse_file(const std::string &path, int64_t limit) { return concat_parts(parse_file_parts(path, limit)); }
+
+// CSR sorted by (user, item): the order of smat_t::load_from_iterator util.h:240-247.  Parallel two-pass counting sort
+// straight from the parsed parts: per-part user histograms -> offsets (file order is kept inside a user, so duplicates
+// stay in file order like the reference's stable handling) -> every part scatters into its own slots.
+inline Csr build_train_csr(int64_t d1, int64_t d2, const std::vector<Triples> &part) {
+    Csr X; X.d1 = d1; X.d2 = d2;
+    const int64_t np = (int64_t)part.size();
+    X.nnz = 0;
+    for (auto &p : part) X.nnz += (int64_t)p.u.size();
     X.row_ptr.assign(d1 + 1, 0);
-    for (size_t e = 0; e < t.u.size(); ++e) {
-        if (t.u[e] < 0 || t.u[e] >= d1 || t.i[e] < 0 || t.i[e] >= d2) throw std::runtime_error("rating id out of range");
-        X.row_ptr[t.u[e] + 1]++;
+    X.item.resize(X.nnz); X.rating.resize(X.nnz);
+    if (np == 0) return X;
+    std::vector<std::vector<int64_t>> off((size_t)np, std::vector<int64_t>());
+    std::atomic<bool> bad(false);
+#pragma omp parallel for schedule(static, 1)
+    for (int64_t t = 0; t < np; ++t) {
+        off[t].assign((size_t)d1, 0);
+        const Triples &p = part[t];
+        for (size_t e = 0; e < p.u.size(); ++e) {
+            if (p.u[e] < 0 || p.u[e] >= d1 || p.i[e] < 0 || p.i[e] >= d2) { bad.store(true); break; }
+            off[t][p.u[e]]++;
+        }
+    }
+    if (bad.load()) throw std::runtime_error("rating id out of range");
+#pragma omp parallel for schedule(static, 4096)
+    for (int64_t u = 0; u < d1; ++u) {
+        int64_t c = 0;
+        for (int64_t t = 0; t < np; ++t) c += off[t][u];
+        X.row_ptr[u + 1] = c;
     }
     for (int64_t u = 0; u < d1; ++u) X.row_ptr[u + 1] += X.row_ptr[u];
-    X.item.resize(X.nnz); X.rating.resize(X.nnz);
-    std::vector<int64_t> fill(X.row_ptr.begin(), X.row_ptr.end() - 1);
-    for (size_t e = 0; e < t.u.size(); ++e) { const int64_t p = fill[t.u[e]]++; X.item[p] = t.i[e]; X.rating[p] = t.r[e]; }
+#pragma omp parallel for schedule(static, 4096)
+    for (int64_t u = 0; u < d1; ++u) {
+        int64_t run = X.row_ptr[u];
+        for (int64_t t = 0; t < np; ++t) { const int64_t c = off[t][u]; off[t][u] = run; run += c; }
+    }
+#pragma omp parallel for schedule(static, 1)
+    for (int64_t t = 0; t < np; ++t) {
+        const Triples &p = part[t];
+        std::vector<int64_t> &o = off[t];
+        for (size_t e = 0; e < p.u.size(); ++e) { const int64_t q = o[p.u[e]]++; X.item[q] = p.i[e]; X.rating[q] = p.r[e]; }
+    }
 #pragma omp parallel for schedule(dynamic, 256)
     for (int64_t u = 0; u < d1; ++u) {
         const int64_t a = X.row_ptr[u], b = X.row_ptr[u + 1];
@@ -133,6 +195,10 @@ inline Csr build_train_csr(int64_t d1, int64_t d2, const Triples &t) {
         for (int64_t e = a; e < b; ++e) { X.item[e] = tmp[e - a].first; X.rating[e] = tmp[e - a].second; }
     }
     return X;
+}
+inline Csr build_train_csr(int64_t d1, int64_t d2, const Triples &t) {
+    std::vector<Triples> one(1, t);
+    return build_train_csr(d1, d2, one);
 }
 
 // convert(testset_t&, d1, d2) util.cpp:250-274, literally: file order, entries lumped while T[cc].i <= j
@@ -164,7 +230,7 @@ inline DataDir load_dir(const std::string &dir) {
     const bool has_test = fscanf(fp, "%ld %1023s", &nnz_t, buf2) == 2;
     fclose(fp);
     DataDir d;
-    d.train = build_train_csr(m, n, parse_file(dir + "/" + buf, nnz));
+    d.train = build_train_csr(m, n, parse_file_parts(dir + "/" + buf, nnz));
     d.has_test = has_test;
     if (has_test) d.test = build_test_csr(m, n, parse_file(dir + "/" + buf2, nnz_t));
     else { d.test.d1 = m; d.test.d2 = n; d.test.row_ptr.assign(m + 1, 0); }

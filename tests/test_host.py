@@ -142,3 +142,26 @@ def test_fast_loader_real_valued_and_errors(tmp_path):
     (d / "meta").write_text("3 4\n1 tr.txt\n")
     with pytest.raises(api.PrimalCRError, match="out of range"):
         api.load_dir(str(d))
+
+
+def test_fast_loader_decimal_parsing_is_correctly_rounded(tmp_path):
+    """The loader's exact-decimal fast path (<= 15 significant digits) and its strtod fallback must both return the
+    correctly rounded double, i.e. what Python's float() -- and the reference's sscanf("%lf") -- give."""
+    rng = np.random.default_rng(11)
+    texts = ["0", "-0", "5", "4.5", "0.1", "-0.3", "3.14159265358979", "123456789012345", "0.000000000000001",
+             "99999.9999999999", "1e-3", "2.5E2", "-7.25e+1", "1234567890.1234567890123", "+3.5", "007.500", ".5", "5."]
+    for _ in range(3000):
+        nd_int = int(rng.integers(0, 9)); nd_frac = int(rng.integers(0, 12))
+        s = "".join(str(int(c)) for c in rng.integers(0, 10, size=nd_int)) or "0"
+        if nd_frac:
+            s += "." + "".join(str(int(c)) for c in rng.integers(0, 10, size=nd_frac))
+        if rng.random() < 0.3:
+            s = "-" + s
+        texts.append(s)
+    d = tmp_path / "d"; d.mkdir()
+    (d / "meta").write_text("1 %d\n%d tr.txt\n" % (len(texts), len(texts)))
+    (d / "tr.txt").write_text("".join("1 %d %s\n" % (j + 1, t) for j, t in enumerate(texts)))
+    a = api.load_dir(str(d), 3)
+    want = np.array([float(t) for t in texts])
+    assert a.train.item.tolist() == list(range(len(texts)))
+    assert np.array_equal(a.train.rating.view(np.uint64), want.view(np.uint64))
