@@ -63,6 +63,12 @@ def main():
                 o["shape"], o["scale"], o["max_len"], "Primal-CR++" if o["solver"] == 2 else "Primal-CR", o["k"], o["nnz"],
                 o["device_gb"], o["sec_per_iter"][-1], o["monotone"], o["recomputed_rel_err"]))
         out.append("")
+    if os.path.exists(P("r01_bench_yahoo_k100_4gpu.json")):
+        y = json.load(open(P("r01_bench_yahoo_k100_4gpu.json")))
+        nc = [k_ for k_ in y["roofline"]["kernels"] if k_["name"] == "nccl_allreduce"]
+        out.append("## Yahoo shape at full size on 4 GPUs (`r01_bench_yahoo_k100_4gpu.json`, `bench.py --gpus 4 --workload yahoo --steps 2 --warmup 1`)\n")
+        out.append("%.4f s per outer iteration (1 GPU: 0.929 s -> %.0f %% parallel efficiency), e2e %.3f s; the %d all-reduces of the 500 MB V-side\nvectors take %.1f ms per iteration (NCCL over NVLink 5).\n" % (
+            y["value"], 100 * 0.9287 / (4 * y["value"]), y["e2e"]["value"], int(nc[0]["launches_per_step"]) if nc else 0, nc[0]["ms_per_step"] if nc else float("nan")))
     open(P("README.md"), "w").write("\n".join(out) + "\n")
 
 
