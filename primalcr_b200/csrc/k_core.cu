@@ -1022,6 +1022,98 @@ __global__ void __launch_bounds__(256) u_cg_step_kernel(UState s, i64 d1, int ld
     }
 }
 
+// Register-resident variants of the two kernels above for ld <= 64 * NV doubles: every lane owns NV 16-byte chunks of
+// the user's k-vectors, each array is read once (all loads issued up front) and written once.
+template <int NV>
+__global__ void __launch_bounds__(256) u_init_vec_kernel(UState s, const double *__restrict__ U, const i64 *__restrict__ row_ptr,
+                                                         const uint8_t *__restrict__ has_pairs, i64 d1, int ld, double lambda) {
+    const int lane = threadIdx.x & 31;
+    const i64 i = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (i >= d1) return;
+    const size_t o = (size_t)i * ld;
+    const int n2 = ld >> 1;
+    const double2 *g2 = reinterpret_cast<const double2 *>(s.g + o), *u2 = reinterpret_cast<const double2 *>(U + o);
+    double2 g[NV], u[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const int c = lane + 32 * q;
+        g[q] = c < n2 ? g2[c] : make_double2(0.0, 0.0);
+        u[q] = c < n2 ? u2[c] : make_double2(0.0, 0.0);
+    }
+    double gg = 0.0, uu = 0.0;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) { gg = fma(g[q].x, g[q].x, gg); gg = fma(g[q].y, g[q].y, gg); uu = fma(u[q].x, u[q].x, uu); uu = fma(u[q].y, u[q].y, uu); }
+    gg = warp_sum(gg); uu = warp_sum(uu);
+    const double prev = lambda / 2.0 * uu + s.loss[i];
+    const bool skip = (gg < 0.0001) || (has_pairs != nullptr && !has_pairs[i]);
+    double2 *d2p = reinterpret_cast<double2 *>(s.delta + o), *r2 = reinterpret_cast<double2 *>(s.rr + o);
+    double2 *p2 = reinterpret_cast<double2 *>(s.p + o), *n2p = reinterpret_cast<double2 *>(s.Unew + o);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const int c = lane + 32 * q;
+        if (c < n2) { d2p[c] = make_double2(0.0, 0.0); r2[c] = make_double2(-g[q].x, -g[q].y); p2[c] = g[q]; n2p[c] = u[q]; }
+    }
+    if (lane == 0) {
+        s.prev_obj[i] = prev; s.obj_new[i] = prev;
+        s.err[i] = sqrt(gg) * 0.01;
+        s.skipped[i] = skip ? 1 : 0; s.cg_active[i] = skip ? 0 : 1; s.ls_active[i] = 0;
+        s.cg_its[i] = 0; s.ls_trials[i] = 0;
+        if (!skip) atomicAdd(&s.counters[0], 1);
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) u_cg_step_vec_kernel(UState s, i64 d1, int ld) {
+    const int lane = threadIdx.x & 31;
+    const i64 i = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (i >= d1) return;
+    if (!s.cg_active[i]) return;
+    const size_t o = (size_t)i * ld;
+    const int n2 = ld >> 1;
+    double2 *p2 = reinterpret_cast<double2 *>(s.p + o), *r2 = reinterpret_cast<double2 *>(s.rr + o);
+    double2 *d2p = reinterpret_cast<double2 *>(s.delta + o);
+    const double2 *h2 = reinterpret_cast<const double2 *>(s.Hp + o);
+    double2 p[NV], hp[NV], rr[NV], dl[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const int c = lane + 32 * q;
+        const double2 z = make_double2(0.0, 0.0);
+        p[q] = c < n2 ? p2[c] : z; hp[q] = c < n2 ? h2[c] : z; rr[q] = c < n2 ? r2[c] : z; dl[q] = c < n2 ? d2p[c] : z;
+    }
+    double pHp = 0.0, rp = 0.0;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        pHp = fma(p[q].x, hp[q].x, pHp); pHp = fma(p[q].y, hp[q].y, pHp);
+        rp = fma(rr[q].x, p[q].x, rp); rp = fma(rr[q].y, p[q].y, rp);
+    }
+    pHp = warp_sum(pHp); rp = warp_sum(rp);
+    const double alpha = -1.0 * rp / pHp;
+    double nr = 0.0, rHp = 0.0;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        dl[q].x = dl[q].x + p[q].x * alpha; dl[q].y = dl[q].y + p[q].y * alpha;
+        rr[q].x = rr[q].x + hp[q].x * alpha; rr[q].y = rr[q].y + hp[q].y * alpha;
+        nr = fma(rr[q].x, rr[q].x, nr); nr = fma(rr[q].y, rr[q].y, nr);
+        rHp = fma(rr[q].x, hp[q].x, rHp); rHp = fma(rr[q].y, hp[q].y, rHp);
+    }
+    nr = warp_sum(nr); rHp = warp_sum(rHp);
+    const int its = s.cg_its[i] + 1;
+    const bool done = (sqrt(nr) < s.err[i]) || (its >= 10);
+    const double beta = rHp / pHp;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const int c = lane + 32 * q;
+        if (c < n2) {
+            d2p[c] = dl[q]; r2[c] = rr[q];
+            if (!done) p2[c] = make_double2(-rr[q].x + p[q].x * beta, -rr[q].y + p[q].y * beta);
+        }
+    }
+    if (lane == 0) {
+        s.cg_its[i] = its;
+        if (done) s.cg_active[i] = 0; else atomicAdd(&s.counters[0], 1);
+    }
+}
+
 __global__ void __launch_bounds__(256) u_ls_begin_kernel(UState s, i64 d1, double stepsize0) {
     const i64 i = (i64)blockIdx.x * 256 + threadIdx.x;
     if (i >= d1) return;
@@ -1093,11 +1185,21 @@ __global__ void __launch_bounds__(256) u_stats_kernel(UState s, const i64 *__res
 
 void k_u_init(Ctx &c, UState &s, const double *U, const i64 *row_ptr, const uint8_t *has_pairs, i64 d1, int ld, double lambda) {
     if (d1 <= 0) return;
-    LAUNCH(c, "u_init", 0.0, u_init_kernel, (unsigned)((d1 + 7) / 8), 256, 0, s, U, row_ptr, has_pairs, d1, ld, lambda);
+    static const bool scalar = getenv("PRIMALCR_U_SCALAR") != nullptr;     // A/B: the first, 8-byte-per-lane kernels
+    const unsigned grid = (unsigned)((d1 + 7) / 8);
+    if (!scalar && ld <= 64) LAUNCH(c, "u_init", 0.0, u_init_vec_kernel<1>, grid, 256, 0, s, U, row_ptr, has_pairs, d1, ld, lambda);
+    else if (!scalar && ld <= 128) LAUNCH(c, "u_init", 0.0, u_init_vec_kernel<2>, grid, 256, 0, s, U, row_ptr, has_pairs, d1, ld, lambda);
+    else if (!scalar && ld <= 256) LAUNCH(c, "u_init", 0.0, u_init_vec_kernel<4>, grid, 256, 0, s, U, row_ptr, has_pairs, d1, ld, lambda);
+    else LAUNCH(c, "u_init", 0.0, u_init_kernel, grid, 256, 0, s, U, row_ptr, has_pairs, d1, ld, lambda);
 }
 void k_u_cg_step(Ctx &c, UState &s, i64 d1, int ld) {
     if (d1 <= 0) return;
-    LAUNCH(c, "u_cg_step", 0.0, u_cg_step_kernel, (unsigned)((d1 + 7) / 8), 256, 0, s, d1, ld);
+    static const bool scalar = getenv("PRIMALCR_U_SCALAR") != nullptr;
+    const unsigned grid = (unsigned)((d1 + 7) / 8);
+    if (!scalar && ld <= 64) LAUNCH(c, "u_cg_step", 0.0, u_cg_step_vec_kernel<1>, grid, 256, 0, s, d1, ld);
+    else if (!scalar && ld <= 128) LAUNCH(c, "u_cg_step", 0.0, u_cg_step_vec_kernel<2>, grid, 256, 0, s, d1, ld);
+    else if (!scalar && ld <= 256) LAUNCH(c, "u_cg_step", 0.0, u_cg_step_vec_kernel<4>, grid, 256, 0, s, d1, ld);
+    else LAUNCH(c, "u_cg_step", 0.0, u_cg_step_kernel, grid, 256, 0, s, d1, ld);
 }
 void k_u_ls_begin(Ctx &c, UState &s, i64 d1) { (void)c; (void)s; (void)d1; }
 void k_u_ls_trial(Ctx &c, UState &s, const double *U, i64 d1, int ld, double stepsize0, int first) {
