@@ -44,7 +44,7 @@ def main():
         out.append("```\n" + open(P("r01_ncu_full_size_summary.txt")).read().strip() + "\n```\n")
         out.append("Reading:\n* `dots_units_kernel<8,7>` (81.2 GB algorithmic per launch, 4.18 ms = 19.4 TB/s): 1.6 GB of DRAM traffic, L2 hit 97 %, l1tex throughput 85 %, L2 throughput 75 % (busiest slice 92 %) -> bound by the L2 -> SM data path and load latency at a full register file, not by HBM.  Fewer shuffles, L1 / L2 cache-policy hints, a shared-memory copy of the hottest rows and 256-bit loads were all measured and changed nothing or lost (profiles/experiments/README.md).\n* `rowsum_kernel<2>` item-major (81.2 GB algorithmic, 5.82 ms = 14 TB/s): 9.0 GB DRAM (U once + the 8-byte coefficient gather through csc2csr + indices + partial sums), L2 hit 83 %, stall reason `long_scoreboard`.\n* `tile_lm_sweep_kernel<1,5,256>` (Hv sweep, 32 B/rating with the packed records): 2.7 GB DRAM in 1.12 ms = 2.4 TB/s, 5 CTAs/SM (48 registers), issue 56 %: latency of the load phase + scalar segmented scan.  `<1,5,512>` / `<1,5,1024>` are the medium (1024 < len <= 2048, two CTAs/SM) and large (<= 4096) tile geometries: 0.21 + 0.09 ms, against 0.47 ms when both shared the 4096-rating tiles (39 % full).\n* `tile_prepare_kernel<5,256>` (4.45 ms; 4.93 before the single-compare exchange): issue slots ~74 % busy -- instruction-bound (64-bit compare-exchange network in registers / shuffles, window binary searches, 5-level count scan); DRAM 5.5 GB per launch (writes dominate: sorted outputs + level-major records).\n* heavy users (`hv_*`, 621 chunks of 2048 ratings): sums 10 us + scan 20 us + look-ups 42 us per sweep on the high-priority side stream, against 144 us for the one-CTA-per-user kernel they replace.\n")
     out.append("## Launch lists (`--metrics gpu__time_duration.sum --clock-control none`)\n")
-    out.append("* `r01_ncu_launches_bench_netflix_k100.csv` — the bench command itself (`python bench.py --steps 1 --warmup 3 --no-cpu-baseline`, full size; the list also holds torch's data-generation kernels, which run before the timed region). Shares over all `pcr::` launches vs the CUDA-event table above: rowsum_kernel 41.0 % (events: 42.3 %), dots_units 33.0 % (33.9 %), lm_sweep Hv 10.5 % (11.5 %), tile_prepare 6.3 % (5.2 %): the kernel shares agree.\n* `r01_ncu_launches_netflix0.2_k100.csv`, `r01_ncu_top_kernels_v1.md` — the FIRST correct path (v1, 0.652 s/iter) at scale 0.2, kept to show where the optimisation started (sweep: 37 warp-instructions per rating; grids sized past occupancy).\n* `experiments/` — measured-and-rejected variants (patches + result tables).\n")
+    out.append("* `r01_ncu_launches_bench_netflix_k100.csv` — the bench command itself (`python bench.py --steps 1 --warmup 3 --no-cpu-baseline`, full size; the list also holds torch's data-generation kernels, which run before the timed region). Shares over all `pcr::` launches vs the CUDA-event table above: rowsum_kernel 41.0 % (events: 42.3 %), dots_units 33.0 % (33.9 %), lm_sweep Hv 10.5 % (11.5 %), tile_prepare 6.3 % (5.2 %): the kernel shares agree.\n* `r01_ncu_launches_netflix0.2_k100.csv`, `r01_ncu_top_kernels_v1.md` — the FIRST correct path (v1, 0.652 s/iter) at scale 0.2, kept to show where the optimisation started (sweep: 37 warp-instructions per rating; grids sized past occupancy).\n* `experiments/` — measured-and-rejected variants (patches + result tables).\n* `r01_trace_one_iteration.txt` — per-launch CUDA-event trace of one outer iteration (`PRIMALCR_TRACE`): 232 launches on the main stream, busy 99.5 % of the 226 ms span (1.2 ms of gaps in total, none above 44 us); the heavy-user kernels run beside them on the side stream.\n")
     out.append("## Multi-GPU (strong scaling, same data set, users sharded by nnz; `r01_bench_netflix_k100_{2,4,8}gpu.json`)\n")
     out.append("| GPUs | s / outer iteration | parallel efficiency t1/(n tn) | e2e s / iteration | objective after 6 iterations |\n|---|---|---|---|---|")
     out.append("| 1 | %.4f | 1.00 | %.3f | %.15g |" % (d["value"], d["e2e"]["value"], d["objective"][-1]))
