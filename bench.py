@@ -352,6 +352,9 @@ def main_ours(args):
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if top and os.path.exists(tpath) and world == 1 and args.workload == "netflix" and args.scale == 1.0 and k == 100:
         roof["traffic"] = json.load(open(tpath)).get(top)      # ncu DRAM bytes per launch of that kernel (one capture)
+        if roof["traffic"]:      # what the HBM actually delivered: far below the peak, the rows come from L2
+            roof["dram_achieved"] = roof["traffic"] / (roof["avg_launch_ms"] / 1e3) / 1e9
+            roof["dram_frac"] = roof["dram_achieved"] / peak
         roof["traffic_note"] = ("algorithmic bytes/launch %.3g >> DRAM traffic/launch: the gathered factor rows are served "
                                 "from L2 (V resident; U walked in 24 MB user blocks), so achieved exceeds the HBM peak" %
                                 roof["bytes_per_launch"])
