@@ -174,6 +174,38 @@ def test_update_V_then_U(name, k, lam, solver):
 
 
 @pytest.mark.parametrize("solver", [2, 1])
+@pytest.mark.parametrize("stepsize", [48.0, 1.0e6])
+def test_line_search_branches(stepsize, solver):
+    """The rarely taken control-flow branches ("control-flow parity"), forced through parameter.stepsize
+    (pmf.h:9-49; not settable from the CLI): 48 -> both line searches halve 5-6 times before accepting (48 and not 64:
+    a halving sequence that hits exactly twice the Newton step makes f(u - 2 delta) = f(u) up to rounding for users
+    whose loss is locally quadratic, and the strict `<` of pcrpp.cpp:808 is then decided by rounding noise); 1e6 -> the first
+    V line search rejects all 20 trials (V kept, the scores of the last trial stay in m, pcrpp.cpp:443) and every user
+    runs 20 U trials and keeps the last one (:814).  Also covers the fall-back of the score / sort reuse in update_V."""
+    ds = dataset("tiny")
+    k, lam = 7, 50.0
+    U, V = init_factors(ds.d1, ds.d2, k)
+    res = ob.oracle().train(solver, to_csr(ds.train), None, U, V, lam, 3, do_predict=0, stepsize=stepsize)
+    e = api.Engine(api.Parameter(solver_type=solver, k=k, lambda_=lam, maxiter=3, stepsize=stepsize))
+    e.set_levels(np.unique(np.rint(ds.train.rating).astype(np.int64)))
+    e.set_train(ds.train); e.set_factors(U, V)
+    assert abs(e.initial_objective() - res["obj"][0]) <= OBJ_TOL * abs(res["obj"][0])
+    seen_rejected = False
+    for i in (1, 2, 3):
+        o = e.outer_iteration()
+        c = e.counters(); cnt = res["counters"][i - 1]
+        assert (c["v_cg_iters"], c["v_ls_trials"], c["v_ls_accepted"]) == tuple(int(x) for x in cnt[:3]), (i, c, cnt)
+        assert (c["u_cg_len_sum"], c["u_ls_len_sum"], c["u_skipped"], c["u_cg_iters"], c["u_ls_trials"]) == tuple(int(x) for x in cnt[3:8]), (i, c, cnt)
+        assert abs(o - res["obj"][i]) <= 1e-8 * abs(res["obj"][i]), (i, o, res["obj"][i])
+        seen_rejected |= c["v_ls_accepted"] == 0
+    assert c["v_ls_trials"] > 1                       # the branch this test is about was really taken
+    assert seen_rejected == (stepsize > 1e3)
+    Ug, Vg = e.get_factors()
+    assert rel(Ug, res["U"]) < 1e-7 and rel(Vg, res["V"]) < 1e-7
+    e.close()
+
+
+@pytest.mark.parametrize("solver", [2, 1])
 @pytest.mark.parametrize("name,k,lam,iters", [("tiny", 7, 50.0, 4), ("ragged", 10, 20.0, 3), ("ml1m", 10, 5000.0, 2),
                                               ("ml1m", 100, 5000.0, 1)])
 def test_training_trajectory(name, k, lam, iters, solver):
