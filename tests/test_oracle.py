@@ -131,3 +131,25 @@ def test_oracle_vs_live_reference_training(solver):
     assert np.all(np.abs(a["obj"] - b["obj"]) <= 1e-12 * np.abs(b["obj"]))
     assert rel(a["U"], b["U"]) < 1e-12 and rel(a["V"], b["V"]) < 1e-12
     assert np.allclose(a["evals"], b["evals"], rtol=0, atol=1e-12)
+
+
+@needs_ref
+@pytest.mark.parametrize("solver", [1, 2])
+@pytest.mark.parametrize("stepsize", [48.0, 1.0e6])
+def test_oracle_vs_live_reference_line_search_branches(stepsize, solver):
+    """The oracle's rarely taken branches against the REAL reference objects: parameter.stepsize = 48 makes both line
+    searches halve several times, 1e6 makes update_V(_new) reject all 20 trials in the first iteration (V kept, stale
+    scores handed to update_U, pcrpp.cpp:443) and every user keep its 20th trial (:814).  Identical factors after three
+    iterations mean identical branch decisions.  (tests/test_gpu_parity.py::test_line_search_branches runs the same
+    cases on the device against the oracle.)"""
+    ds = dataset("tiny")
+    k, lam = 7, 50.0
+    U = ob.ref_initial(ds.d1, k); V = ob.ref_initial(ds.d2, k)
+    X = to_csr(ds.train)
+    a = ob.oracle().train(solver, X, None, U, V, lam, 3, do_predict=0, stepsize=stepsize)
+    b = ob.reference().train(solver, X, None, U, V, lam, 3, do_predict=0, stepsize=stepsize)
+    assert np.all(np.abs(a["obj"] - b["obj"]) <= 1e-12 * np.abs(b["obj"]))
+    assert rel(a["U"], b["U"]) < 1e-12 and rel(a["V"], b["V"]) < 1e-12
+    cnt = a["counters"]
+    assert all(int(c[1]) > 1 for c in cnt)                                # V line search really took several trials
+    assert (int(cnt[0][2]) == 0) == (stepsize > 1e3)                      # ... and was rejected outright with 1e6
