@@ -5,11 +5,18 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU implementation
 
 One JSON line on stdout (rank 0).  A "step" is one outer iteration over the whole (sharded) rating set:
-  value  = device-timed seconds per outer iteration with ratings/factors resident in HBM (max over ranks);
-  e2e    = the same metric through the reference-facing call (host CSR + host U,V in, K iterations, host U,V
-           out), host<->device copies and the one-time CSR/CSC preparation inside the timed region;
-  roofline      = dominant kernel's algorithmic bytes / CUDA-event time vs the measured HBM peak;
-  cpu_baseline  = the reference `omp-pmf-train` (oracle/_ref) on a bounded user sample, extrapolated.
+  value  = device-timed seconds per outer iteration with ratings/factors resident in HBM (max over ranks), iterations
+           W+1 .. W+K from the reference init (the driver's window);
+  e2e    = the same metric through the reference-facing call (host CSR + host U,V in, W+K iterations from the same init,
+           host U,V out), host<->device copies and the one-time CSR/CSC preparation inside the timed region, divided by
+           W+K; `e2e.device_same_window` is the device-timed mean over the SAME iterations 1 .. W+K, so
+           e2e.value - e2e.device_same_window is exactly what the copies and the setup cost per iteration;
+           `e2e.shim` is the call through the real C++ drop-in (reference containers in pageable memory, oracle/shim_e2e.cpp);
+  roofline      = dominant kernel's algorithmic bytes / CUDA-event time vs the measured HBM peak (`frac_kind`
+                  "algorithmic_vs_hbm": it exceeds 1 when the gathered rows come from L2), with the ncu DRAM bytes and L2
+                  counters of the same kernel beside it (profiles/r02_traffic.json, regenerated from this round's capture);
+  cpu_baseline  = the reference's race-free `omp-pmf-train-rf` (oracle/_ref) on a bounded user sample, extrapolated;
+  parity        = the engine vs the unmodified reference (race-free harness) on the first ~2 M ratings of the same data.
 """
 import argparse
 import json
@@ -101,10 +108,28 @@ def reference_init_cached(n, k):
 
 # --------------------------------------------------------------------------------------------- CPU reference arm
 
+# the race-free build (obj_u_new made loop-local, oracle/Makefile): with -n > 1 the stock binary's line search reads
+# another thread's objective (pcrpp.cpp:822-832), so its work per iteration is not reproducible
+REF_EXE = "omp-pmf-train-rf"
+# measured on the GPU box's 16 host cores (round 1): ~1.6e-6 s per rating and iteration at k=100
+REF_SEC_PER_RATING_ITER_16C = 1.6e-6
+
+
+def reference_sample_nnz(args, iters, nnz, budget_s):
+    """Ratings in the reference's timing sample: 10 % of the workload unless `iters` iterations of it would
+    not finish within `budget_s`; never below 2 M."""
+    if args.ref_sample_nnz > 0:
+        return min(args.ref_sample_nnz, nnz)
+    cores = os.cpu_count() or 1
+    per = REF_SEC_PER_RATING_ITER_16C * 16.0 / min(cores, 16) * (args.k / 100.0)
+    fit = int(budget_s / max(iters, 1) / per)
+    return int(min(nnz, max(2_000_000, min(nnz // 10, fit))))
+
+
 def run_reference_cli(ds_sample, k, lam, iters, threads):
     """Times the reference's own omp-pmf-train (oracle/_ref) on `ds_sample`; returns per-iteration seconds."""
     from primalcr_b200.data import write_reference_dir
-    exe = os.path.join(ROOT, "oracle", "_ref", "omp-pmf-train")
+    exe = os.path.join(ROOT, "oracle", "_ref", REF_EXE)
     with tempfile.TemporaryDirectory() as tmp:
         d = os.path.join(tmp, "data")
         write_reference_dir(d, ds_sample)
@@ -131,29 +156,33 @@ def run_oracle_port(ds_sample, k, lam, iters):
     return np.array(per)
 
 
-def cpu_baseline(ds, args, iters, sample_nnz):
-    """Reference CPU time per outer iteration on a bounded user sample, extrapolated linearly in #ratings."""
+def head_sample(ds, sample_nnz):
     from primalcr_b200.data import Dataset, Ratings
     rp = ds.train.row_ptr
     n_users = int(np.searchsorted(rp, min(sample_nnz, ds.train.nnz), side="left"))
     n_users = max(1, min(n_users, ds.d1))
-    sample = Dataset(ds.train.slice_users(0, n_users), Ratings.empty(n_users, ds.d2), "sample")
+    return Dataset(ds.train.slice_users(0, n_users), Ratings.empty(n_users, ds.d2), "sample"), n_users
+
+
+def cpu_baseline(ds, args, iters, sample_nnz):
+    """Reference CPU time per outer iteration on a bounded user sample, extrapolated linearly in #ratings."""
+    sample, n_users = head_sample(ds, sample_nnz)
     cores = os.cpu_count() or 1
-    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "omp-pmf-train"))
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", REF_EXE))
     t = time.time()
     if have_ref:
         per, _ = run_reference_cli(sample, args.k, args.lam, iters, cores)
         kind = "reference"
-    else:
-        per = run_oracle_port(sample, args.k, args.lam, iters)
+    else:       # oracle/_ref is built wherever /root/reference is mounted and travels with the repo: this is the fallback
+        per = run_oracle_port(sample, args.k, args.lam, iters)       # for a tree that never saw the reference
         kind, cores = "port", 1
     factor = ds.train.nnz / max(sample.train.nnz, 1)
     log("[bench] cpu %s: %d users / %d ratings, per-iter %s s, x%.1f extrapolation, %.1fs total" % (
         kind, n_users, sample.train.nnz, np.round(per, 3).tolist(), factor, time.time() - t))
     return {"per_iter_sample_s": per.tolist(), "factor": factor, "kind": kind, "cores": cores,
-            "sample": "first %d users (%d ratings, %.4f of the workload) of the same synthetic set, omp-pmf-train "
-                      "-s 2 -k %d -l %g -p 0 -n %d; seconds per iteration scaled by nnz ratio %.1f" % (
-                          n_users, sample.train.nnz, sample.train.nnz / ds.train.nnz, args.k, args.lam, cores, factor)}
+            "sample": "first %d users (%d ratings, %.4f of the workload) of the same synthetic set, %s (race-free build "
+                      "of the reference) -s 2 -k %d -l %g -p 0 -n %d; seconds per iteration scaled by nnz ratio %.1f" % (
+                          n_users, sample.train.nnz, sample.train.nnz / ds.train.nnz, REF_EXE, args.k, args.lam, cores, factor)}
 
 
 def main_reference(args):
@@ -162,7 +191,7 @@ def main_reference(args):
         return 0
     ds = make_workload(args, "cpu" if args.scale <= 0.05 else _gen_device())
     iters = args.warmup + args.steps
-    cb = cpu_baseline(ds, args, iters, args.ref_sample_nnz)
+    cb = cpu_baseline(ds, args, iters, reference_sample_nnz(args, iters, ds.train.nnz, budget_s=170.0))
     per = np.array(cb["per_iter_sample_s"])[args.warmup:]
     value = float(per.mean() * cb["factor"])
     line = {
@@ -172,6 +201,10 @@ def main_reference(args):
         "config": workload_config(args, ds),
         "cpu_baseline": {"value": value, "unit": "s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]},
         "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "extrapolation": {"factor": cb["factor"], "measured_s_per_step_on_sample": float(per.mean()),
+                          "note": "value = measured seconds per iteration on the sample x nnz ratio (the path is linear in "
+                                  "the ratings; a full-size CPU iteration takes minutes, %d of them would not fit a bench "
+                                  "run), so steps x value exceeds this run's wall time by that factor" % iters},
     }
     _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
     return 0
@@ -191,6 +224,66 @@ def workload_config(args, ds):
             "solver": "Primal-CR++", "k": args.k, "lambda": args.lam, "d1": ds.d1, "d2": ds.d2, "nnz": ds.train.nnz,
             "parallelism": "users sharded over %d GPU(s) by nnz, V replicated, NCCL allreduce of d2 x k sums" % args.gpus,
             "l2_policy": "working set (>= 9 GB of ratings + factors per pass at full size) exceeds the 126 MB L2; no flush needed"}
+
+
+# --------------------------------------------------------------------------------------------- parity / shim legs
+
+def parity_check(ds, args, device, sample_nnz=2_000_000, iters=2):
+    """The engine against the UNMODIFIED reference (race-free harness, all host threads) on the first ~2 M ratings of the
+    bench's own data, same init: objective per outer iteration at full precision and training NDCG@10 / pairwise error."""
+    from oracle import bindings as ob
+    from primalcr_b200 import api
+    R = ob.reference_rf()
+    if R is None:
+        return {"unavailable": "oracle/_ref/libref_harness_rf.so not built (needs /root/reference at build time)"}
+    sample, n_users = head_sample(ds, sample_nnz)
+    X = ob.Csr(sample.d1, sample.d2, sample.train.row_ptr, sample.train.item.astype(np.int64), sample.train.rating)
+    U0 = api.reference_init(sample.d1, args.k); V0 = api.reference_init(sample.d2, args.k)
+    t = time.time()
+    ref = R.train(2, X, None, U0, V0, args.lam, iters, do_predict=1, threads=os.cpu_count() or 1)
+    t_ref = time.time() - t
+    e = api.Engine(api.Parameter(solver_type=api.PCRPP, k=args.k, lambda_=args.lam, maxiter=iters, device=device))
+    e.set_levels(np.arange(1, 6, dtype=np.int64)); e.set_train(sample.train); e.set_factors(U0, V0)
+    objs = [e.initial_objective()]; evals = [e.eval(0)]
+    for _ in range(iters):
+        objs.append(e.outer_iteration()); evals.append(e.eval(0))
+    e.close()
+    objs = np.array(objs); evals = np.array(evals)
+    out = {"obj_rel_err": float(np.max(np.abs(objs - ref["obj"]) / np.abs(ref["obj"]))),
+           "ndcg_abs_err": float(np.max(np.abs(evals[:, 1] - ref["evals"][:, 1]))),
+           "pairwise_err_abs_err": float(np.max(np.abs(evals[:, 0] - ref["evals"][:, 0]))),
+           "tolerance": {"obj_rel": 1e-6, "ndcg_abs": 1e-4},
+           "objective": objs.tolist(), "reference_objective": ref["obj"].tolist(),
+           "sample": "first %d users (%d ratings) of the bench data, k=%d, %d outer iterations, reference = unmodified pcrpp.cpp "
+                     "(race-free objects) on %d threads (%.0f s)" % (n_users, sample.train.nnz, args.k, iters, os.cpu_count() or 1, t_ref)}
+    out["ok"] = bool(out["obj_rel_err"] < 1e-6 and out["ndcg_abs_err"] < 1e-4)
+    log("[bench] parity vs reference on %d ratings: obj rel err %.2e, ndcg abs err %.2e" % (
+        sample.train.nnz, out["obj_rel_err"], out["ndcg_abs_err"]))
+    return out
+
+
+def shim_e2e(shard, args, iters):
+    """e2e through the real drop-in: oracle/_ref/shim-e2e fills the reference's own containers (smat_t, mat_t =
+    vector<vector<double>> in pageable memory, initial()) and calls pcrpp() = our shim + libprimalcr_b200.so once."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "shim-e2e")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/shim-e2e not built (needs /root/reference at build time)"}
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+        path = os.path.join(tmp, "csr.bin")
+        with open(path, "wb") as f:
+            np.array([shard.d1, shard.d2, shard.nnz], np.int64).tofile(f)
+            shard.row_ptr.astype(np.int64).tofile(f); shard.item.astype(np.int32).tofile(f); shard.rating.astype(np.float64).tofile(f)
+        r = subprocess.run([exe, path, str(args.k), str(args.lam), str(iters)], capture_output=True, text=True)
+    m = re.search(r"SHIM_E2E seconds=(\S+) iters=(\d+)", r.stdout)
+    if r.returncode != 0 or not m:
+        return {"unavailable": "shim-e2e failed: rc=%d %s" % (r.returncode, r.stderr[-300:])}
+    total = float(m.group(1))
+    objs = [float(x.group(1)) for x in re.finditer(r"^Iter \d+ time \S+ obj (\S+)", r.stdout, re.M)]
+    log("[bench] shim e2e: pcrpp() call %.3f s for %d iterations" % (total, iters))
+    return {"value": total / iters, "unit": "s", "call_seconds": total, "iterations": iters, "objective_last": objs[-1] if objs else None,
+            "note": "wall time of ONE pcrpp(smat_t&, mat_t&, mat_t&, testset_t&, parameter&) call through primalcr_b200/shim/"
+                    "pcr_shim.cpp with the reference's containers in pageable memory (flattening vector<vector<double>>, "
+                    "H2D, setup, Iter-0 objective + %d iterations, D2H, un-flattening) / iterations" % iters}
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -267,6 +360,9 @@ def main_ours(args):
     eng.set_train_raw(shard.d1, shard.d2, shard.nnz, h_rp, h_it, h_ra)
     eng.set_factors(h_U, h_V)
     stream = torch.cuda.ExternalStream(eng.stream_ptr(), device=torch.device("cuda", local))
+    ev_init = torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev_init.record(stream)            # start of the window the e2e leg covers: "Iter 0" objective + iterations 1 .. W+K
     obj0 = eng.initial_objective()
     objs = [obj0]
     for _ in range(args.warmup):
@@ -287,6 +383,8 @@ def main_ours(args):
     sampler.window[1] = time.perf_counter()
     sampler.stop_flag = True; sampler.join()
     sec = max_over_ranks(ev0.elapsed_time(ev1) / 1e3) / args.steps
+    n_all = args.warmup + args.steps
+    sec_same_window = max_over_ranks(ev_init.elapsed_time(ev1) / 1e3) / n_all
     launches = eng.launch_count() - launches0
     prof = eng.profile()
     eng.profile_enable(False)
@@ -294,11 +392,11 @@ def main_ours(args):
     eng.close(); del eng
     torch.cuda.empty_cache()
 
-    # ---------------- end-to-end leg: host buffers in, K iterations, host factors out
+    # ---------------- end-to-end leg: host buffers in, the SAME W+K iterations from the same init, host factors out
     outU = torch.empty_like(h_U).pin_memory(); outV = torch.empty_like(h_V).pin_memory()
     barrier()
     t0 = time.perf_counter()
-    e2 = new_engine(args.steps)
+    e2 = new_engine(n_all)
     t1 = time.perf_counter()
     e2.set_train_raw(shard.d1, shard.d2, shard.nnz, h_rp, h_it, h_ra)
     t2 = time.perf_counter()
@@ -309,12 +407,13 @@ def main_ours(args):
     e2.get_factors(outU, outV)
     barrier()
     t5 = time.perf_counter()
-    e2e_sec = max_over_ranks(t5 - t0) / args.steps
+    e2e_sec = max_over_ranks(t5 - t0) / n_all
     e2e_phases = {"create": t1 - t0, "set_train": t2 - t1, "set_factors": t3 - t2, "run": t4 - t3, "get_factors": t5 - t4}
     log("[bench] rank %d e2e phases (s): %s" % (rank, {k_: round(v_, 4) for k_, v_ in e2e_phases.items()}))
     e2.close()
-    h2d = (h_rp.numel() * 8 + h_it.numel() * 4 + h_ra.numel() * 8 + h_U.numel() * 8 + h_V.numel() * 8) / args.steps
-    d2h = (outU.numel() * 8 + outV.numel() * 8) / args.steps
+    h2d = (h_rp.numel() * 8 + h_it.numel() * 4 + h_ra.numel() * 8 + h_U.numel() * 8 + h_V.numel() * 8) / n_all
+    d2h = (outU.numel() * 8 + outV.numel() * 8) / n_all
+    torch.cuda.empty_cache()
 
     per_rank = None
     if world > 1:      # per-rank kernel totals (load balance of the user shards), gathered before the ranks part ways
@@ -349,28 +448,43 @@ def main_ours(args):
                     avg_launch_ms=hot[top]["ms"] / hot[top]["launches"],
                     bytes_per_launch=hot[top]["bytes"] / hot[top]["launches"],
                     share_of_step=hot[top]["ms"] / 1e3 / (sec * args.steps))
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if top and os.path.exists(tpath) and world == 1 and args.workload == "netflix" and args.scale == 1.0 and k == 100:
-        roof["traffic"] = json.load(open(tpath)).get(top)      # ncu DRAM bytes per launch of that kernel (one capture)
-        if roof["traffic"]:      # what the HBM actually delivered: far below the peak, the rows come from L2
-            roof["dram_achieved"] = roof["traffic"] / (roof["avg_launch_ms"] / 1e3) / 1e9
-            roof["dram_frac"] = roof["dram_achieved"] / peak
-        roof["traffic_note"] = ("algorithmic bytes/launch %.3g >> DRAM traffic/launch: the gathered factor rows are served "
-                                "from L2 (V resident; U walked in 24 MB user blocks), so achieved exceeds the HBM peak" %
-                                roof["bytes_per_launch"])
+    roof["frac_kind"] = ("algorithmic_vs_hbm: SURVEY 8d's logical row touches per launch / launch time / measured HBM peak; "
+                         "the gathered rows are served from L2/L1, so this is NOT an HBM utilisation and may exceed 1 -- "
+                         "see dram_frac and l2 for what the memory system delivered")
+    # ncu figures of THIS round's tree (one `ncu --set full` capture per kernel + one dram-bytes launch list of a whole
+    # iteration; tools/gpu/r02_capture.sh, summarised by tools/ncu_summary.py traffic): a profiler cannot run inside a bench run
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    same_workload = world == 1 and args.workload == "netflix" and args.scale == 1.0 and k == 100
+    if top and same_workload and top in traffic.get("kernels", {}):
+        tk = traffic["kernels"][top]
+        roof["traffic"] = tk["dram_bytes_per_launch"]        # dram__bytes_read.sum + dram__bytes_write.sum per launch
+        roof["dram_achieved"] = roof["traffic"] / (roof["avg_launch_ms"] / 1e3) / 1e9   # what the HBM actually delivered
+        roof["dram_frac"] = roof["dram_achieved"] / peak
+        roof["l2"] = {"lts_throughput_pct": tk.get("lts_throughput_pct"), "l2_hit_pct": tk.get("l2_hit_pct"),
+                      "l1tex_hit_pct": tk.get("l1tex_hit_pct"), "dram_read_bytes_per_launch": tk.get("dram_read_bytes_per_launch"),
+                      "note": "the binding resource of the N*k gathers is the L2 -> SM path, not HBM"}
+        roof["traffic_source"] = traffic.get("_note")
+    it_dram = traffic.get("iteration", {}).get("dram_bytes") if same_workload else None
     roof.update(peak_source=peak_src,
                 iteration={"b_alg_bytes": b_alg, "achieved": b_alg / sec / 1e9 * 1.0, "frac": b_alg / sec / 1e9 / peak / world,
-                           "note": "B_alg = passes*[N(8k+12)+8k*d1] + sorts*32N (SURVEY 8d); frac is per GPU",
+                           "frac_kind": "algorithmic_vs_hbm",
+                           "dram_bytes": it_dram, "dram_frac": (it_dram / sec / 1e9 / peak) if it_dram else None,
+                           "note": "B_alg = passes*[N(8k+12)+8k*d1] + sorts*32N (SURVEY 8d); frac is per GPU; dram_bytes = ncu "
+                                   "dram read+write summed over every launch of one outer iteration",
                            "counters": its[-1]})
     kern = sorted(((v["ms"], n, v["launches"], v["bytes"]) for n, v in prof.items()), reverse=True)
     roof["kernels"] = [{"name": n, "ms_per_step": ms / args.steps, "launches_per_step": l / args.steps,
                         "gbs": (b / (ms / 1e3) / 1e9 if b > 0 and ms > 0 else None)} for ms, n, l, b in kern[:40]]
 
-    cb = None
+    cb = parity = shim = None
     if world == 1 and not args.no_cpu_baseline:
-        c = cpu_baseline(ds, args, 2, args.ref_sample_nnz)
+        c = cpu_baseline(ds, args, 2, reference_sample_nnz(args, 2, ds.train.nnz, budget_s=40.0))
         per = np.array(c["per_iter_sample_s"])
         cb = {"value": float(per[-1] * c["factor"]), "unit": "s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]}
+        parity = parity_check(ds, args, local)
+    if world == 1 and not args.no_shim_e2e:
+        shim = shim_e2e(shard, args, n_all)
 
     line = {
         "metric": METRIC, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -378,10 +492,14 @@ def main_ours(args):
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, ds),
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_sec, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "phases_s": e2e_phases,
-                "note": "whole pcrpp()-style call (upload CSR+U+V, build CSC, %d iterations, download U+V) / iterations" % args.steps},
+                "phases_s": e2e_phases, "iterations": n_all, "device_same_window": sec_same_window,
+                "shim": shim,
+                "note": "whole pcrpp()-style call through the C ABI from pinned host buffers (upload CSR+U+V, build CSC and work "
+                        "lists, Iter-0 objective + iterations 1..%d from the reference init, download U+V) / %d; "
+                        "device_same_window = device-timed mean of the same iterations with everything resident "
+                        "(`value` covers iterations %d..%d only)" % (n_all, n_all, args.warmup + 1, n_all)},
         "gpu_launches": int(launches),
-        "roofline": roof, "cpu_baseline": cb, "per_rank": per_rank,
+        "roofline": roof, "cpu_baseline": cb, "parity": parity, "per_rank": per_rank,
         "objective": objs, "device_bytes": dev_bytes,
     }
     _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
@@ -405,9 +523,14 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="user/rating subsample factor of the named shape")
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--lam", type=float, default=5000.0)
-    ap.add_argument("--ref-sample-nnz", type=int, default=2_000_000)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample-nnz", type=int, default=0,
+                    help="ratings in the reference's timing sample (0: 10 %% of the workload, less if that would not fit the run)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline and parity legs")
+    ap.add_argument("--no-shim-e2e", action="store_true", help="skip the e2e run through the C++ drop-in shim")
     args = ap.parse_args()
+    global METRIC
+    if not (args.workload == "netflix" and args.k == 100):
+        METRIC = "sec_per_outer_iter_primalcrpp_k%d_%s_shape" % (args.k, args.workload)
     if args.impl == "reference":
         return main_reference(args)
     return main_ours(args)

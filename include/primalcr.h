@@ -50,6 +50,8 @@ typedef struct {
     int    ndcg_k;      /* param.ndcg_k      : default 10                                 */
     int    do_predict;  /* param.do_predict  : evaluate error/NDCG every iteration        */
     int    device;      /* CUDA device ordinal for this engine                            */
+    int    threads;     /* param.threads     : only echoed in the "using N threads. " log line
+                           (pcrpp.cpp:855, pcr.cpp:631); the GPU path has no use for it (default 4) */
 } primalcr_config;
 
 /* integer control-flow counters of the last outer iteration (they must match the oracle's) */

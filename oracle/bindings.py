@@ -222,6 +222,21 @@ def reference():
     return _ref
 
 
+_ref_rf = None
+
+
+def reference_rf():
+    """The reference harness over the race-free objects (obj_u_new made loop-local, see oracle/Makefile): the build to use
+    with threads > 1.  None when oracle/_ref was never built."""
+    global _ref_rf
+    if _ref_rf is None:
+        lib = _load(os.path.join(HERE, "_ref", "libref_harness_rf.so"))
+        if lib is None:
+            return None
+        _ref_rf = _Lib(lib, "ref_")
+    return _ref_rf
+
+
 def ref_initial(n, k):
     out = np.zeros((n, k))
     reference().lib.ref_initial(out, n, k)

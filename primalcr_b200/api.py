@@ -29,7 +29,8 @@ class PrimalCRError(RuntimeError):
 
 class _Config(C.Structure):
     _fields_ = [("solver", C.c_int), ("k", C.c_int), ("lambda_", C.c_double), ("stepsize", C.c_double),
-                ("maxiter", C.c_int), ("ndcg_k", C.c_int), ("do_predict", C.c_int), ("device", C.c_int)]
+                ("maxiter", C.c_int), ("ndcg_k", C.c_int), ("do_predict", C.c_int), ("device", C.c_int),
+                ("threads", C.c_int)]
 
 
 class Counters(C.Structure):
@@ -130,6 +131,19 @@ def _ptr(a):
     return a.data_ptr()   # torch tensor (pinned host memory in bench.py)
 
 
+def _require_factor(a, rows: int, k: int, name: str):
+    """The C ABI reads / writes rows*k doubles through a raw pointer: insist on a C-contiguous float64 (rows, k) buffer."""
+    if isinstance(a, np.ndarray):
+        ok = a.dtype == np.float64 and a.flags.c_contiguous and a.flags.writeable and a.shape == (rows, k)
+    else:       # torch CPU tensor
+        import torch
+        ok = isinstance(a, torch.Tensor) and a.dtype == torch.float64 and a.device.type == "cpu" and a.is_contiguous() \
+            and tuple(a.shape) == (rows, k)
+    if not ok:
+        raise PrimalCRError("%s must be a C-contiguous float64 array of shape (%d, %d), got %s %s" % (
+            name, rows, k, getattr(a, "dtype", type(a)), tuple(getattr(a, "shape", ()))))
+
+
 def reference_init(n: int, k: int) -> np.ndarray:
     """initial() util.cpp:80-93 -- the default-seeded N(0,1) stream of the reference CLI (host code, libstdc++)."""
     out = np.empty((n, k), np.float64)
@@ -178,7 +192,7 @@ class Parameter:
     """``class parameter`` pmf.h:9-49 (the fields pcr()/pcrpp() read), same names and defaults."""
     solver_type: int = PCRPP
     k: int = 10
-    threads: int = 4          # accepted for CLI compatibility; has no meaning on the GPU
+    threads: int = 4          # echoed in the "using N threads. " log line only; has no meaning on the GPU
     maxiter: int = 10
     lambda_: float = 5000.0   # `lambda` in the reference
     stepsize: float = 1.0
@@ -198,7 +212,7 @@ class Engine:
         cfg.solver = int(solver if solver is not None else param.solver_type)
         cfg.k = int(param.k); cfg.lambda_ = float(param.lambda_); cfg.stepsize = float(param.stepsize)
         cfg.maxiter = int(param.maxiter); cfg.ndcg_k = int(param.ndcg_k); cfg.do_predict = int(param.do_predict)
-        cfg.device = int(param.device)
+        cfg.device = int(param.device); cfg.threads = int(param.threads)
         self.k = cfg.k
         self._h = C.c_void_p()
         self._L = L
@@ -245,11 +259,15 @@ class Engine:
     def set_factors(self, U, V):
         if isinstance(U, np.ndarray):
             U = np.ascontiguousarray(U, np.float64); V = np.ascontiguousarray(V, np.float64)
+        _require_factor(U, self.d1, self.k, "U"); _require_factor(V, self.d2, self.k, "V")
         self._check(self._L.primalcr_set_factors(self._h, _ptr(U), _ptr(V)))
 
     def get_factors(self, U=None, V=None):
+        """Writes d1*k and d2*k doubles through the raw pointers of U and V: both must be C-contiguous float64
+        (d1, k) / (d2, k) buffers (numpy arrays or torch CPU tensors); anything else raises instead of corrupting memory."""
         if U is None:
             U = np.empty((self.d1, self.k)); V = np.empty((self.d2, self.k))
+        _require_factor(U, self.d1, self.k, "U"); _require_factor(V, self.d2, self.k, "V")
         self._check(self._L.primalcr_get_factors(self._h, _ptr(U), _ptr(V)))
         return U, V
 
@@ -367,6 +385,7 @@ class Engine:
 # ----------------------------------------------------------------------------- the reference's solver interface
 
 def _solve(solver, X: Ratings, U: np.ndarray, V: np.ndarray, T: Ratings | None, param: Parameter, log=print):
+    _require_factor(U, X.d1, param.k, "U"); _require_factor(V, X.d2, param.k, "V")     # in/out buffers: checked before any work
     eng = Engine(param, solver=solver)
     try:
         eng.set_train(X)

@@ -80,7 +80,7 @@ int main(int argc, char **argv) {
         switch (argv[i - 1][1]) {
             case 's': cfg.solver = atoi(argv[i]); break;
             case 'k': cfg.k = atoi(argv[i]); break;
-            case 'n': threads = atoi(argv[i]); break;
+            case 'n': threads = atoi(argv[i]); cfg.threads = threads; break;
             case 'l': cfg.lambda = atof(argv[i]); break;
             case 't': cfg.maxiter = atoi(argv[i]); break;
             case 'p': cfg.do_predict = atoi(argv[i]); break;
@@ -105,14 +105,18 @@ int main(int argc, char **argv) {
         const size_t s = p.rfind('/');
         model = (s == std::string::npos ? p : p.substr(s + 1)) + ".model";
     }
-    FILE *model_fp = fopen(model.c_str(), "wb");
+    // The reference opens (and truncates) the model file before loading anything (pmf-train.cpp:252-259).  We write to
+    // <model>.tmp and rename() after a successful solve instead: `-w m.model data m.model` keeps training the same file,
+    // and a bad data dir or a failed GPU init never leaves a zero-length file over a good model.
+    const std::string model_tmp = model + ".tmp";
+    FILE *model_fp = fopen(model_tmp.c_str(), "wb");
     if (!model_fp) { fprintf(stderr, "can't open output file %s\n", model.c_str()); exit(1); }
 #ifdef _OPENMP
     omp_set_num_threads(threads > 0 ? threads : 1);
 #endif
     pcrhost::DataDir data;
     try { data = pcrhost::load_dir(input); }
-    catch (const std::exception &ex) { fprintf(stderr, "primalcr-train: %s\n", ex.what()); return 1; }
+    catch (const std::exception &ex) { fprintf(stderr, "primalcr-train: %s\n", ex.what()); fclose(model_fp); remove(model_tmp.c_str()); return 1; }
     const pcrhost::Csr &X = data.train, &T = data.test;
     const int k = cfg.k;
     std::vector<double> U((size_t)X.d1 * k), V((size_t)X.d2 * k);
@@ -124,6 +128,7 @@ int main(int argc, char **argv) {
         long r1 = 0, k1 = 0, r2 = 0, k2 = 0;
         if (!wf || !read_matrix(wf, U, r1, k1) || !read_matrix(wf, V, r2, k2) || r1 != X.d1 || r2 != X.d2 || k1 != k || k2 != k) {
             fprintf(stderr, "can't warm start from %s (need %ld x %d and %ld x %d)\n", warm.c_str(), (long)X.d1, k, (long)X.d2, k);
+            fclose(model_fp); remove(model_tmp.c_str());
             exit(1);
         }
         fclose(wf);
@@ -145,6 +150,9 @@ int main(int argc, char **argv) {
     if (!getenv("PRIMALCR_NO_TEXT_DUMP")) write_text("V" + suffix + ".txt", V, X.d2, k);
     write_matrix(model_fp, U, X.d1, k);
     write_matrix(model_fp, V, X.d2, k);
-    fclose(model_fp);
+    if (fclose(model_fp) != 0 || rename(model_tmp.c_str(), model.c_str()) != 0) {
+        fprintf(stderr, "can't write model file %s\n", model.c_str());
+        return 1;
+    }
     return 0;
 }

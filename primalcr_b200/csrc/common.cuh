@@ -215,6 +215,6 @@ static const int L_CAP = 4096;   // large class  (1024 threads, shared memory)
 #endif
 static const int ROWSUM_CHUNK = PCR_ROWSUM_CHUNK;
 static const int PAIR_TJ = 256;  // j elements per pair work item
-static const int MAX_LEVELS = 32;
+static const int MAX_LEVELS = 256;  // levels are uint8 indices; more than 8 levels -> per-user T-vector kernels (k_core.cu)
 
 }  // namespace pcr

@@ -112,7 +112,10 @@ struct Engine {
         memset(&counters, 0, sizeof(counters));
         memset(&us, 0, sizeof(us));
         PCR_REQUIRE(cfg.solver == 1 || cfg.solver == 2, "solver must be 1 (Primal-CR) or 2 (Primal-CR++)");
-        PCR_REQUIRE(cfg.k >= 1 && cfg.k <= 512, "rank k out of range [1, 512]");
+        PCR_REQUIRE(cfg.k >= 1 && cfg.k <= 256, "rank k out of range [1, 256]");
+        // NDCG@k keeps the top-k of a user in a 64-entry shared-memory table (k_pairs.cu eval_users_kernel); the reference's
+        // min(ndcg_k, len) with ndcg_k <= 0 divides 0 by 0 (util.cpp:513-531)
+        PCR_REQUIRE(cfg.ndcg_k >= 1 && cfg.ndcg_k <= 64, "ndcg_k out of range [1, 64]");
         int ndev = 0;
         cudaError_t e = cudaGetDeviceCount(&ndev);
         if (e != cudaSuccess || ndev == 0)
@@ -222,7 +225,7 @@ struct Engine {
     }
 
     void set_levels(const i64 *vals, int n) {
-        PCR_REQUIRE(n >= 1 && n <= MAX_LEVELS, "number of rating levels must be in [1, 32]");
+        PCR_REQUIRE(n >= 1 && n <= MAX_LEVELS, "number of rating levels must be in [1, 256]");
         levels.assign(vals, vals + n);
         for (int i = 1; i < n; ++i) PCR_REQUIRE(levels[i] > levels[i - 1], "level table must be strictly ascending");
         levels_user_set = true;
@@ -246,39 +249,52 @@ struct Engine {
         d1 = d1_; d2 = d2_;
         build_csr_common(X, d1_, nnz, row_ptr, item, rating);
         lap("upload CSR + pair tiles");
-        // ---- rating levels (find_levels pcrpp.cpp:38-49, as one global order-preserving table)
-        if (!levels_user_set) {
-            i64 lo = 0, hi = 0; bool any = false;
-            std::vector<i64> distinct;
-            for (i64 e = 0; e < nnz; ++e) {
-                const i64 v = llround(rating[e]);
-                if (!any) { lo = hi = v; any = true; }
-                if (v < lo) lo = v; if (v > hi) hi = v;
-                if (hi - lo >= 4096) break;
-            }
-            if (!any) { lo = hi = 0; }
-            if (hi - lo + 1 <= MAX_LEVELS) {
-                // a superset of the levels present is harmless: an empty level contributes 0*x - 0
-                for (i64 v = lo; v <= hi; ++v) distinct.push_back(v);
-            } else {
+        // ---- rating levels (find_levels pcrpp.cpp:38-49, as one global order-preserving table).  Primal-CR (-s 1) never
+        // looks at levels (pcr.cpp compares the exact ratings), so any rating scale is accepted there.
+        X.level = pool.alloc<uint8_t>((size_t)nnz);
+        if (cfg.solver == 1) {
+            levels.assign(1, 0); T = 1;
+            PCR_CUDA(cudaMemsetAsync(X.level, 0, (size_t)(nnz > 0 ? nnz : 1), stream));
+        } else {
+            if (!levels_user_set) {
+                i64 lo = 0, hi = 0; bool any = false;
                 for (i64 e = 0; e < nnz; ++e) {
                     const i64 v = llround(rating[e]);
-                    auto it = std::lower_bound(distinct.begin(), distinct.end(), v);
-                    if (it == distinct.end() || *it != v) distinct.insert(it, v);
-                    PCR_REQUIRE((int)distinct.size() <= MAX_LEVELS, "more than 32 distinct rating levels");
+                    if (!any) { lo = hi = v; any = true; }
+                    if (v < lo) lo = v; if (v > hi) hi = v;
+                    if (hi - lo >= 65536) break;
                 }
+                if (!any) { lo = hi = 0; }
+                std::vector<i64> distinct;
+                if (hi - lo + 1 <= 8) {
+                    // a superset of the levels present is harmless: an empty level contributes 0*x - 0
+                    for (i64 v = lo; v <= hi; ++v) distinct.push_back(v);
+                } else if (hi - lo < 65536) {
+                    std::vector<uint8_t> seen((size_t)(hi - lo + 1), 0);
+                    for (i64 e = 0; e < nnz; ++e) seen[(size_t)(llround(rating[e]) - lo)] = 1;
+                    for (i64 v = lo; v <= hi; ++v) if (seen[(size_t)(v - lo)]) distinct.push_back(v);
+                } else {
+                    for (i64 e = 0; e < nnz; ++e) {
+                        const i64 v = llround(rating[e]);
+                        auto it = std::lower_bound(distinct.begin(), distinct.end(), v);
+                        if (it == distinct.end() || *it != v) distinct.insert(it, v);
+                        if ((int)distinct.size() > MAX_LEVELS) break;
+                    }
+                }
+                // more than 8 levels: the per-user T-vector kernels take over from the tile kernels (any T up to 256, the
+                // range of the uint8 level index); the reference itself has no cap (find_levels is a per-user set)
+                PCR_REQUIRE((int)distinct.size() <= MAX_LEVELS, "more than 256 distinct lround(rating) levels (Primal-CR++ level index is 8 bits; -s 1 has no limit)");
+                levels = distinct;
             }
-            levels = distinct;
+            T = (int)levels.size();
+            i64 *tab = upload_vec(levels);
+            int *bad = pool.alloc<int>(1);
+            PCR_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), stream));
+            k_levels(ctx, X.rating, nnz, tab, T, X.level, bad);
+            PCR_CUDA(cudaMemcpyAsync(h_counters, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            sync();
+            PCR_REQUIRE(h_counters[0] == 0, "a rating rounds to a level that is not in the level table");
         }
-        T = (int)levels.size();
-        i64 *tab = upload_vec(levels);
-        int *bad = pool.alloc<int>(1);
-        PCR_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), stream));
-        X.level = pool.alloc<uint8_t>((size_t)nnz);
-        k_levels(ctx, X.rating, nnz, tab, T, X.level, bad);
-        PCR_CUDA(cudaMemcpyAsync(h_counters, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        sync();
-        PCR_REQUIRE(h_counters[0] == 0, "a rating rounds to a level that is not in the level table");
         lap("levels");
         // ---- size classes, heavy scratch
         std::vector<int32_t> cls[3];
@@ -673,7 +689,12 @@ struct Engine {
         PCR_REQUIRE(has_train && has_factors, "engine needs a training set and factors");
         bind();
     }
-    void ensure_scores() { if (!scores_valid) { scores(U, V, m, nullptr); scores_valid = true; meta_valid = false; loss_matches_m = false; } }
+    void ensure_scores() {
+        if (scores_valid) return;
+        scores(U, V, m, nullptr);
+        scores_valid = true; meta_valid = false; loss_matches_m = false;
+        last_m_is_stale = false;      // m is comp_m(U, V) again, no longer the scores of a rejected V trial
+    }
     void ensure_meta() { ensure_scores(); if (cfg.solver == 2 && !meta_valid) prepare(m, nullptr); }
 
     // ------------------------------------------------------------------ stage entry points
@@ -864,7 +885,8 @@ struct Engine {
         require_ready();
         auto say = [&](const std::string &s) { if (log && rank == 0) log(s.c_str(), lctx); };
         say(std::string(cfg.solver == 2 ? "running PrimalCR++ ndcg_k is " : "running PrimalCR ndcg_k is ") + std::to_string(cfg.ndcg_k));
-        say("using " + std::to_string(world) + " B200 GPU(s). ");
+        say("using " + std::to_string(cfg.threads) + " threads. ");          // verbatim, pcrpp.cpp:855 / pcr.cpp:631
+        if (rank == 0) fprintf(stderr, "primalcr_b200: users sharded over %d GPU(s)\n", world);   // not part of the stdout contract
         double now_obj = objective_current();
         say("Iter 0 time 0 obj " + fmt_g(now_obj));
         auto do_eval = [&]() {
@@ -913,7 +935,7 @@ const char *primalcr_version(void) { return "primalcr_b200 0.1.0 (sm_100a)"; }
 void primalcr_default_config(primalcr_config *cfg) {
     if (!cfg) return;
     cfg->solver = PRIMALCR_SOLVER_PCRPP; cfg->k = 10; cfg->lambda = 5000; cfg->stepsize = 1.0;
-    cfg->maxiter = 10; cfg->ndcg_k = 10; cfg->do_predict = 1; cfg->device = 0;
+    cfg->maxiter = 10; cfg->ndcg_k = 10; cfg->do_predict = 1; cfg->device = 0; cfg->threads = 4;
 }
 
 int primalcr_create(primalcr_engine **out, const primalcr_config *cfg) {

@@ -22,6 +22,23 @@ namespace pcr {
 #define FULL 0xffffffffu
 #endif
 
+// which rating levels a user holds: a 256-bit map in shared memory (levels are uint8 indices into the global table)
+__device__ __forceinline__ void lvl_mark(unsigned *m, int l) {
+    const unsigned bit = 1u << (l & 31);
+    if (!(reinterpret_cast<volatile unsigned *>(m)[l >> 5] & bit)) atomicOr(&m[l >> 5], bit);
+}
+__device__ __forceinline__ bool lvl_has(const unsigned *m, int t) { return (m[t >> 5] >> (t & 31)) & 1u; }
+__device__ __forceinline__ bool lvl_any_below(const unsigned *m, int t) {
+    for (int w = 0; w < (t >> 5); ++w) if (m[w]) return true;
+    return (m[t >> 5] & ((1u << (t & 31)) - 1u)) != 0u;
+}
+__device__ __forceinline__ int lvl_count(const unsigned *m) {
+    int c = 0;
+#pragma unroll
+    for (int w = 0; w < MAX_LEVELS / 32; ++w) c += __popc(m[w]);
+    return c;
+}
+
 // minimum resident CTAs per SM requested from ptxas for the two N*k kernels (register budget = 65536 / (256 * MINB))
 #ifndef PCR_ROWSUM_MINB
 #define PCR_ROWSUM_MINB 4
@@ -239,129 +256,6 @@ __global__ void __launch_bounds__(256, PCR_ROWSUM_MINB) rowsum_kernel(const int3
     }
 }
 
-// ------------------------------------------------------------------ K4 (bulk-async variant): rows staged by the TMA unit
-// EXPERIMENT, off by default (PRIMALCR_ROWSUM_TMA=1 enables it; parity-tested).  Every lane asks the TMA unit for one
-// whole row (cp.async.bulk, global -> shared memory, completion on an mbarrier), two stages per warp, and the FMAs read
-// the rows from shared memory.  Measured on B200 (Netflix-shape, k=100, 800-byte rows): 11.4 ms per item-major pass
-// against 6.6 ms for the register variant, i.e. about one 800-byte bulk copy per 33 cycles per SM -- the per-request cost
-// of cp.async.bulk is too high for rows this short.  Kept for longer rows (k >= 400) and as a record of the measurement.
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-static const int TMA_WARPS = 8;                 // warps per CTA
-static const int TMA_WARP_BYTES = 25 * 1024;    // shared memory per warp (two stages)
-
-template <int NCH>
-__global__ void __launch_bounds__(TMA_WARPS * 32, 1) rowsum_tma_kernel(const int32_t *__restrict__ un_seg,
-                                                                        const i64 *__restrict__ un_start,
-                                                                        const i64 *__restrict__ un_end, i64 n_units,
-                                                                        unsigned long long *__restrict__ ticket,
-                                                                        const int32_t *__restrict__ ridx,
-                                                                        const int32_t *__restrict__ widx,
-                                                                        const double *__restrict__ w,
-                                                                        const double *__restrict__ M, int ld, int nch, int rs,
-                                                                        const uint8_t *__restrict__ active,
-                                                                        double *__restrict__ partial) {
-    extern __shared__ __align__(128) unsigned char tma_smem[];
-    __shared__ __align__(8) uint64_t bars[TMA_WARPS][2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t rb = (uint32_t)nch * 16u;                 // payload bytes of one row
-    unsigned char *stage0 = tma_smem + (size_t)warp * TMA_WARP_BYTES;
-    unsigned char *stage1 = stage0 + (size_t)rs * rb;
-    if (lane == 0) { mbar_init(&bars[warp][0], 1); mbar_init(&bars[warp][1], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    uint32_t phase0 = 0, phase1 = 0;
-    for (;;) {
-        unsigned long long tk = 0;
-        if (lane == 0) tk = atomicAdd(ticket, 1ull);
-        const i64 u = (i64)__shfl_sync(FULL, tk, 0);
-        if (u >= n_units) break;
-        const int seg = un_seg[u];
-        if (active && !active[seg]) continue;
-        const i64 b = un_start[u], e = un_end ? un_end[u] : un_start[u + 1];
-        double2 acc[NCH];
-#pragma unroll
-        for (int q = 0; q < NCH; ++q) acc[q] = make_double2(0.0, 0.0);
-        const i64 nb = (e - b + rs - 1) / rs;                 // batches of rs rows
-        // prologue: batch 0 -> stage 0
-        double wcur = 0.0, wnext = 0.0;
-        {
-            const i64 me = b + lane;
-            const bool on = lane < rs && me < e;
-            int ri = 0;
-            if (on) { ri = ridx[me]; wcur = widx ? w[widx[me]] : w[me]; }
-            const int cnt = (int)((e - b) < rs ? (e - b) : rs);
-            if (lane == 0) mbar_expect_tx(&bars[warp][0], (uint32_t)cnt * rb);
-            __syncwarp();
-            if (on) bulk_g2s(stage0 + (size_t)lane * rb, M + (size_t)ri * ld, rb, &bars[warp][0]);
-        }
-        for (i64 bi = 0; bi < nb; ++bi) {
-            const int cur = (int)(bi & 1);
-            // prefetch batch bi+1 into the other stage (its previous contents were consumed in iteration bi-1)
-            if (bi + 1 < nb) {
-                const i64 base = b + (bi + 1) * rs;
-                const i64 me = base + lane;
-                const bool on = lane < rs && me < e;
-                int ri = 0;
-                wnext = 0.0;
-                if (on) { ri = ridx[me]; wnext = widx ? w[widx[me]] : w[me]; }
-                const int cnt = (int)((e - base) < rs ? (e - base) : rs);
-                uint64_t *bar = &bars[warp][cur ^ 1];
-                if (lane == 0) mbar_expect_tx(bar, (uint32_t)cnt * rb);
-                __syncwarp();
-                if (on) bulk_g2s((cur ? stage0 : stage1) + (size_t)lane * rb, M + (size_t)ri * ld, rb, bar);
-            }
-            // consume batch bi
-            const i64 base = b + bi * rs;
-            const int cnt = (int)((e - base) < rs ? (e - base) : rs);
-            if (cur == 0) { mbar_wait(&bars[warp][0], phase0); phase0 ^= 1u; }
-            else          { mbar_wait(&bars[warp][1], phase1); phase1 ^= 1u; }
-            const unsigned char *st = cur ? stage1 : stage0;
-#pragma unroll 4
-            for (int j = 0; j < cnt; ++j) {
-                const double ww = __shfl_sync(FULL, wcur, j);
-                const double2 *row = reinterpret_cast<const double2 *>(st + (size_t)j * rb);
-#pragma unroll
-                for (int q = 0; q < NCH; ++q) {
-                    const int ci = lane + 32 * q;
-                    if (ci < nch) {
-                        const double2 x = row[ci];
-                        acc[q].x = fma(ww, x.x, acc[q].x);
-                        acc[q].y = fma(ww, x.y, acc[q].y);
-                    }
-                }
-            }
-            wcur = wnext;
-            __syncwarp();        // every lane is done reading this stage before it is refilled
-        }
-        double2 *o = reinterpret_cast<double2 *>(partial + (size_t)u * ld);
-#pragma unroll
-        for (int q = 0; q < NCH; ++q) { const int ci = lane + 32 * q; if (ci < nch) o[ci] = acc[q]; }
-    }
-}
-
 // out[seg] = lambda*x[seg] + partial[first unit] + partial[second unit] + ...   (fixed order => deterministic)
 // One warp per segment; a lane owns up to 4 double2 chunks of the row and walks the unit list once with all of them in
 // flight (16-byte loads).  kp = payload columns (even), the padding up to ld is kept exactly zero.
@@ -417,23 +311,10 @@ void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_
     const char *rs_name = widx ? "rowsum_items" : (active ? "rowsum_users_active" : "rowsum_users");
     if (n_units > 0) {
         PCR_CUDA(cudaMemsetAsync(c.ticket, 0, sizeof(unsigned long long), c.stream));
-        static const bool use_tma = getenv("PRIMALCR_ROWSUM_TMA") != nullptr && atoi(getenv("PRIMALCR_ROWSUM_TMA")) != 0;
-        const int rb = nch * 16;
-        int rs = TMA_WARP_BYTES / 2 / rb;
-        if (rs > 32) rs = 32;
-        if (use_tma && rs >= 4) {
-            const size_t sm = (size_t)TMA_WARPS * TMA_WARP_BYTES;
-            const unsigned g = (unsigned)std::min<i64>((i64)c.sms, (n_units + TMA_WARPS - 1) / TMA_WARPS);
-#define RT(N) { PCR_CUDA(cudaFuncSetAttribute(rowsum_tma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-                LAUNCH(c, rs_name, bytes, rowsum_tma_kernel<N>, g, TMA_WARPS * 32, sm, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, rs, active, partial); }
-            switch (NCH) { case 1: RT(1) break; case 2: RT(2) break; case 3: RT(3) break; default: RT(4) break; }
-#undef RT
-        } else {
 #define RS(N) { const unsigned grid = resident_grid(rowsum_kernel<N>, 256, 0, c.sms, (n_units + 7) / 8); \
                 LAUNCH(c, rs_name, bytes, rowsum_kernel<N>, grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); }
-            switch (NCH) { case 1: RS(1) break; case 2: RS(2) break; case 3: RS(3) break; default: RS(4) break; }
+        switch (NCH) { case 1: RS(1) break; case 2: RS(2) break; case 3: RS(3) break; default: RS(4) break; }
 #undef RS
-        }
     }
     if (n_seg > 0)
         LAUNCH(c, "rowsum_finalize", 0.0, rowsum_finalize_kernel, grid_for(n_seg, 8, c.sms * 8), 256, 0, seg_unit_ptr, seg_unit_idx, n_seg,
@@ -532,7 +413,7 @@ __global__ void __launch_bounds__(THREADS) windows_kernel(const int32_t *__restr
                                                           int32_t *__restrict__ g_cnt) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ int wsum[THREADS / 32 + 1];
-    __shared__ unsigned s_mask;
+    __shared__ unsigned s_mask[MAX_LEVELS / 32];
     const int u = users[blockIdx.x];
     if (active && !active[u]) return;
     const i64 start = row_ptr[u];
@@ -540,7 +421,7 @@ __global__ void __launch_bounds__(THREADS) windows_kernel(const int32_t *__restr
     const int tid = threadIdx.x;
     const double *keys;
     int *cnt;
-    if (tid == 0) s_mask = 0u;
+    if (tid < MAX_LEVELS / 32) s_mask[tid] = 0u;
     if (n <= smem_cap) {
         double *k = reinterpret_cast<double *>(smraw);
         for (int j = tid; j < n; j += THREADS) k[j] = s_g[start + j];
@@ -551,7 +432,6 @@ __global__ void __launch_bounds__(THREADS) windows_kernel(const int32_t *__restr
         cnt = g_cnt + heavy_off[u];
     }
     __syncthreads();
-    unsigned mymask = 0u;
     for (int j = tid; j < n; j += THREADS) {
         const double sj = keys[j];
         const double hi = __dadd_rn(sj, 1.0), lo = __dadd_rn(sj, -1.0);
@@ -563,14 +443,11 @@ __global__ void __launch_bounds__(THREADS) windows_kernel(const int32_t *__restr
         const int lb = a;
         ub_g[start + j] = ub; lb_g[start + j] = lb;
         lo_g[start + j] = 0;  hi_g[start + j] = 0;
-        mymask |= 1u << lev_g[start + j];
+        lvl_mark(s_mask, lev_g[start + j]);
     }
-    mymask = __reduce_or_sync(FULL, mymask);
-    if ((tid & 31) == 0 && mymask) atomicOr(&s_mask, mymask);
     __syncthreads();
-    const unsigned mask = s_mask;
     for (int t = 1; t < T; ++t) {
-        if (!(mask & ((1u << t) | (1u << (t - 1))))) continue;     // block-uniform
+        if (!lvl_has(s_mask, t) && !lvl_has(s_mask, t - 1)) continue;     // block-uniform
         for (int j = tid; j < n; j += THREADS) cnt[j] = lev_g[start + j] >= t ? 1 : 0;
         __syncthreads();
         block_excl_scan<int, THREADS>(cnt, n, wsum);
@@ -649,7 +526,7 @@ __global__ void __launch_bounds__(THREADS) sweep_coeff_kernel(const int32_t *__r
                                                               double *__restrict__ g_acc) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ double wsum[THREADS / 32 + 1];
-    __shared__ unsigned s_mask;
+    __shared__ unsigned s_mask[MAX_LEVELS / 32];
     const int u = users[blockIdx.x];
     if (active && !active[u]) return;
     const i64 start = row_ptr[u];
@@ -662,21 +539,17 @@ __global__ void __launch_bounds__(THREADS) sweep_coeff_kernel(const int32_t *__r
         const i64 off = heavy_off[u];
         v = g_v + off; P = g_p + off; acc = g_acc + off;
     }
-    if (tid == 0) s_mask = 0u;
+    if (tid < MAX_LEVELS / 32) s_mask[tid] = 0u;
     __syncthreads();
-    unsigned mymask = 0u;
     for (int j = tid; j < n; j += THREADS) {
         v[j] = MODE == 0 ? s_g[start + j] : b_g[pos_g[start + j]];
         acc[j] = 0.0;
-        mymask |= 1u << lev_g[start + j];
+        lvl_mark(s_mask, lev_g[start + j]);
     }
-    mymask = __reduce_or_sync(FULL, mymask);
-    if ((tid & 31) == 0 && mymask) atomicOr(&s_mask, mymask);
     __syncthreads();
-    const unsigned mask = s_mask;
-    if ((mask & (mask - 1)) != 0) {          // at least two levels present, otherwise every c_j is 0
+    if (lvl_count(s_mask) >= 2) {          // at least two levels present, otherwise every c_j is 0
         for (int t = 0; t < T; ++t) {
-            if (!(mask & (1u << t))) continue;
+            if (!lvl_has(s_mask, t)) continue;
             for (int j = tid; j < n; j += THREADS) P[j] = lev_g[start + j] == t ? v[j] : 0.0;
             __syncthreads();
             block_excl_scan<double, THREADS>(P, n, wsum);
@@ -739,7 +612,7 @@ __global__ void __launch_bounds__(THREADS) sweep_obj_kernel(const int32_t *__res
                                                             double *__restrict__ g_p2, double *__restrict__ g_acc) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ double wsum[THREADS / 32 + 1];
-    __shared__ unsigned s_mask;
+    __shared__ unsigned s_mask[MAX_LEVELS / 32];
     const int u = users[blockIdx.x];
     if (active && !active[u]) return;
     const i64 start = row_ptr[u];
@@ -752,18 +625,14 @@ __global__ void __launch_bounds__(THREADS) sweep_obj_kernel(const int32_t *__res
         const i64 off = heavy_off[u];
         P1 = g_p1 + off; P2 = g_p2 + off; acc = g_acc + off;
     }
-    if (tid == 0) s_mask = 0u;
+    if (tid < MAX_LEVELS / 32) s_mask[tid] = 0u;
     __syncthreads();
-    unsigned mymask = 0u;
-    for (int j = tid; j < n; j += THREADS) { acc[j] = 0.0; mymask |= 1u << lev_g[start + j]; }
-    mymask = __reduce_or_sync(FULL, mymask);
-    if ((tid & 31) == 0 && mymask) atomicOr(&s_mask, mymask);
+    for (int j = tid; j < n; j += THREADS) { acc[j] = 0.0; lvl_mark(s_mask, lev_g[start + j]); }
     __syncthreads();
-    const unsigned mask = s_mask;
-    if ((mask & (mask - 1)) != 0) {
+    if (lvl_count(s_mask) >= 2) {
         for (int t = 1; t < T; ++t) {
-            if (!(mask & (1u << t))) continue;
-            if (!(mask & ((1u << t) - 1u))) continue;      // nothing below level t
+            if (!lvl_has(s_mask, t)) continue;
+            if (!lvl_any_below(s_mask, t)) continue;      // nothing below level t
             for (int j = tid; j < n; j += THREADS) {
                 const double d = s_g[start + j] - 1.0;
                 const bool on = lev_g[start + j] == t;
@@ -1201,7 +1070,6 @@ void k_u_cg_step(Ctx &c, UState &s, i64 d1, int ld) {
     else if (!scalar && ld <= 256) LAUNCH(c, "u_cg_step", 0.0, u_cg_step_vec_kernel<4>, grid, 256, 0, s, d1, ld);
     else LAUNCH(c, "u_cg_step", 0.0, u_cg_step_kernel, grid, 256, 0, s, d1, ld);
 }
-void k_u_ls_begin(Ctx &c, UState &s, i64 d1) { (void)c; (void)s; (void)d1; }
 void k_u_ls_trial(Ctx &c, UState &s, const double *U, i64 d1, int ld, double stepsize0, int first) {
     if (d1 <= 0) return;
     if (first) LAUNCH(c, "u_ls_begin", 0.0, u_ls_begin_kernel, (unsigned)((d1 + 255) / 256), 256, 0, s, d1, stepsize0);

@@ -40,9 +40,9 @@ __global__ void levels_kernel(const double *__restrict__ rating, i64 nnz, const 
                               uint8_t *__restrict__ out, int *__restrict__ bad) {
     for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (i64)gridDim.x * blockDim.x) {
         const i64 v = llround(rating[e]);
-        int k = 0;
-        while (k < T && table[k] != v) ++k;
-        if (k == T) { *bad = 1; k = 0; }
+        int k = 0, hi = T;                      // the table is strictly ascending: lower bound
+        while (k < hi) { const int mid = (k + hi) >> 1; if (table[mid] < v) k = mid + 1; else hi = mid; }
+        if (k == T || table[k] != v) { *bad = 1; k = 0; }
         out[e] = (uint8_t)k;
     }
 }

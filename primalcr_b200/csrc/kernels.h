@@ -82,7 +82,6 @@ struct UState {
 void k_u_init(Ctx &c, UState &s, const double *U, const i64 *row_ptr, const uint8_t *has_pairs, i64 d1, int ld,
               double lambda);
 void k_u_cg_step(Ctx &c, UState &s, i64 d1, int ld);
-void k_u_ls_begin(Ctx &c, UState &s, i64 d1);       // cg_active is dead: ls_active = !skipped, step = stepsize
 void k_u_ls_trial(Ctx &c, UState &s, const double *U, i64 d1, int ld, double stepsize0, int first);
 void k_u_ls_check(Ctx &c, UState &s, i64 d1, int ld, double lambda, int last);
 void k_u_commit(Ctx &c, UState &s, double *U, i64 d1, int ld);

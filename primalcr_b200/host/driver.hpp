@@ -46,7 +46,8 @@ inline int gpus_from_env() {
 // U (d1 x k) and V (d2 x k) row-major, updated in place -- like the reference's mat_t& U, mat_t& V
 inline void solve(const primalcr_config &base, const FlatCsr &X, const FlatCsr &XT, double *U, double *V, int gpus) {
     const int k = base.k;
-    const std::vector<int64_t> levels = global_levels(X);
+    // Primal-CR (-s 1) compares the exact ratings (pcr.cpp:23): no level table, any rating scale
+    const std::vector<int64_t> levels = base.solver == PRIMALCR_SOLVER_PCRPP ? global_levels(X) : std::vector<int64_t>();
     std::vector<int64_t> bounds(gpus + 1, 0);            // contiguous user shards balanced by nnz
     for (int r = 1; r < gpus; ++r) {
         const int64_t target = (int64_t)((double)X.nnz * r / gpus);
@@ -61,7 +62,7 @@ inline void solve(const primalcr_config &base, const FlatCsr &X, const FlatCsr &
         cfg.device = rank;
         primalcr_engine *e = nullptr;
         PCRHOST_CK(primalcr_create(&e, &cfg));
-        PCRHOST_CK(primalcr_set_levels(e, levels.data(), (int)levels.size()));
+        if (!levels.empty()) PCRHOST_CK(primalcr_set_levels(e, levels.data(), (int)levels.size()));
         PCRHOST_CK(primalcr_comm_init(e, rank, gpus, gpus > 1 ? uid : nullptr));
         const int64_t u0 = bounds[rank], u1 = bounds[rank + 1];
         auto shard = [&](const FlatCsr &F, std::vector<int64_t> &rp) {

@@ -50,6 +50,7 @@ void solve(int solver, smat_t &R, mat_t &U, mat_t &V, testset_t &T, parameter &p
     primalcr_config cfg; primalcr_default_config(&cfg);
     cfg.solver = solver; cfg.k = k; cfg.lambda = param.lambda; cfg.stepsize = param.stepsize;
     cfg.maxiter = param.maxiter; cfg.ndcg_k = param.ndcg_k; cfg.do_predict = param.do_predict;
+    cfg.threads = param.threads;
     pcrhost::FlatCsr fx{d1, d2, nnz, row_ptr.data(), item.data(), rating.data()};
     pcrhost::FlatCsr ft{d1, d2, cc, rpt.data(), itt.data(), rat.data()};
     pcrhost::solve(cfg, fx, ft, Uf.data(), Vf.data(), pcrhost::gpus_from_env());
