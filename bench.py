@@ -274,6 +274,9 @@ def shim_e2e(shard, args, iters):
             np.array([shard.d1, shard.d2, shard.nnz], np.int64).tofile(f)
             shard.row_ptr.astype(np.int64).tofile(f); shard.item.astype(np.int32).tofile(f); shard.rating.astype(np.float64).tofile(f)
         r = subprocess.run([exe, path, str(args.k), str(args.lam), str(iters)], capture_output=True, text=True)
+    for l in r.stderr.splitlines():
+        if l.startswith("[primalcr"):
+            log("[bench] shim " + l)
     m = re.search(r"SHIM_E2E seconds=(\S+) iters=(\d+)", r.stdout)
     if r.returncode != 0 or not m:
         return {"unavailable": "shim-e2e failed: rc=%d %s" % (r.returncode, r.stderr[-300:])}

@@ -101,6 +101,12 @@ int primalcr_update_U(primalcr_engine *e, double *now_obj);       /* update_U_ne
 int primalcr_outer_iteration(primalcr_engine *e, double *now_obj);/* update_V then update_U                     */
 /* compute_pairwise_error_ndcg util.cpp:434-542; which = 0 training set, 1 test set */
 int primalcr_eval(primalcr_engine *e, int which, double *pairwise_error, double *ndcg);
+/* the same evaluation with the integer pair-error count of every user written to err_per_user[d1] (any pointer may be NULL).
+   method 0: the reference's all-pairs count (util.cpp:467-479), O(len^2); method 1: the identical integer obtained from the
+   Primal-CR++ sorted state in O(len * levels) (training set, integer ratings, <= 8 levels; PRIMALCR_EARG otherwise).
+   primalcr_eval picks method 1 whenever it applies. */
+int primalcr_eval_error_counts(primalcr_engine *e, int which, int method, int64_t *err_per_user, double *pairwise_error,
+                               double *ndcg);
 /* whole driver with the reference's stdout lines (one callback per line, without the newline) */
 int primalcr_run(primalcr_engine *e, primalcr_log_fn log, void *ctx);
 int primalcr_get_counters(primalcr_engine *e, primalcr_counters *out);

@@ -46,7 +46,8 @@ SYMBOLS = [
     "primalcr_default_config", "primalcr_create", "primalcr_destroy", "primalcr_last_error", "primalcr_version",
     "primalcr_set_levels", "primalcr_set_train_csr", "primalcr_set_test_csr", "primalcr_set_factors",
     "primalcr_get_factors", "primalcr_nccl_unique_id", "primalcr_comm_init", "primalcr_initial_objective",
-    "primalcr_update_V", "primalcr_update_U", "primalcr_outer_iteration", "primalcr_eval", "primalcr_run",
+    "primalcr_update_V", "primalcr_update_U", "primalcr_outer_iteration", "primalcr_eval", "primalcr_eval_error_counts",
+    "primalcr_run",
     "primalcr_get_counters", "primalcr_scores", "primalcr_set_scores", "primalcr_sort_segments",
     "primalcr_level_counts", "primalcr_num_levels", "primalcr_objective", "primalcr_grad_V", "primalcr_hv_V",
     "primalcr_grad_U", "primalcr_hv_U", "primalcr_stream", "primalcr_launch_count", "primalcr_profile_enable",
@@ -93,6 +94,7 @@ def lib():
     for name in ("initial_objective", "objective", "update_V", "update_U", "outer_iteration"):
         getattr(L, "primalcr_" + name).argtypes = [vp, C.POINTER(C.c_double)]
     L.primalcr_eval.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.primalcr_eval_error_counts.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.primalcr_run.argtypes = [vp, LOG_FN, vp]
     L.primalcr_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.primalcr_scores.argtypes = [vp, f64p]
@@ -300,6 +302,14 @@ class Engine:
         a, b = C.c_double(), C.c_double()
         self._check(self._L.primalcr_eval(self._h, which, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def eval_error_counts(self, which: int = 0, method: int = 0):
+        """(pairwise error, NDCG, integer pair-error count per user); method 0 all pairs, 1 sorted state (Primal-CR++ train set)."""
+        n = self.d1
+        cnt = np.zeros(max(n, 1), np.int64)
+        a, b = C.c_double(), C.c_double()
+        self._check(self._L.primalcr_eval_error_counts(self._h, which, method, cnt.ctypes.data, C.byref(a), C.byref(b)))
+        return a.value, b.value, cnt[:n]
 
     def run(self, log=print):
         lines = []

@@ -203,6 +203,16 @@ struct HeavyLM {
     i64 htot = 0;
 };
 
+// work list of the heavy-user segmented sort (k_hsort.cu): chunks of HEAVY_CHUNK ratings, one scratch (score, position) pair
+struct HeavySortPlan {
+    int n_users = 0, n_chunks = 0, max_passes = 0;
+    const i64 *begin = nullptr, *end = nullptr;   // [n_users] absolute rating range of the user
+    const i64 *off = nullptr;                     // [n_users] offset of the user inside the scratch pair
+    const int32_t *chunk_user = nullptr;          // [n_chunks] index into begin/end/off
+    const int32_t *chunk_lo = nullptr;            // [n_chunks] first rating of the chunk inside its user
+    double *tmp_s = nullptr; int32_t *tmp_pos = nullptr;   // [sum of heavy lens] ping-pong partner of SortedMeta::s / pos
+};
+
 static const int TILE_CAP = 1024;        // ratings per tile of consecutive users (k_tiles.cu)
 static const int TILE_MAX_USERS = 128;   // users per tile
 static const int TILE_CAP_M = 2048;      // medium tiles: 512 threads, two CTAs per SM (most users above TILE_CAP are below 2048:

@@ -75,22 +75,28 @@ struct Engine {
     bool levels_user_set = false;
     DevCsr X, XT;
     bool has_train = false, has_test = false, has_factors = false, use_tiles = true;
+    bool ratings_integer = false;     // every training rating equals its lround: levels order ratings like the exact doubles
+    i64 *ev_err_user = nullptr;
     // CSC of the training set (by item)
     i64 *col_ptr = nullptr; int32_t *csc_user = nullptr, *csc2csr = nullptr;
     int32_t *cu_seg = nullptr; i64 *cu_start = nullptr, *cu_end = nullptr; i64 n_cunits = 0; i64 *col_unit_ptr = nullptr;
     int32_t *col_unit_idx = nullptr; int n_user_blocks = 1, n_item_blocks = 1;
+    // multi-GPU: the item-major pass runs one ITEM GROUP (balanced by ratings) at a time, so that the all-reduce of group g
+    // (comm stream) overlaps the row sums of group g+1 (compute stream)
+    static const int MAX_AR_GROUPS = 16;
+    int n_groups = 1; std::vector<i64> grp_unit0, grp_item0;
+    cudaStream_t comm_stream = nullptr; cudaEvent_t ev_grp[MAX_AR_GROUPS] = {nullptr}, ev_comm = nullptr;
     // factors (padded leading dimension ld)
     double *U = nullptr, *V = nullptr;
     // per-rating work buffers
     double *m = nullptr, *b = nullptr, *cbuf = nullptr;
     SortedMeta meta;
-    int32_t *iota = nullptr;
     bool scores_valid = false, meta_valid = false;
     // heavy-user scratch of the one-CTA-per-user kernels (allocated on demand: T > 8, or the score-order outputs for tests)
     double *h_v = nullptr, *h_p1 = nullptr, *h_p2 = nullptr, *h_acc = nullptr; int32_t *h_cnt = nullptr;
     HeavyLM hv;                       // chunk-parallel heavy-user path (k_heavy.cu)
     bool heavy_chunked = false, heavy_windows_valid = false;
-    void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+    HeavySortPlan hsort;              // hand-written segmented sort of the heavy users (k_hsort.cu)
     // V-side vectors [d2 x ld]
     double *g = nullptr, *delta = nullptr, *rr = nullptr, *p = nullptr, *Hp = nullptr, *Vnew = nullptr;
     double *partial = nullptr;
@@ -134,6 +140,14 @@ struct Engine {
             PCR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
             PCR_CUDA(cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, prio_hi));
         }
+        {
+            int prio_lo = 0, prio_hi = 0;
+            PCR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            // the collective's few CTAs must get SM slots while a persistent row-sum grid of the next group is resident
+            PCR_CUDA(cudaStreamCreateWithPriority(&comm_stream, cudaStreamNonBlocking, prio_hi));
+            for (int q = 0; q < MAX_AR_GROUPS; ++q) PCR_CUDA(cudaEventCreateWithFlags(&ev_grp[q], cudaEventDisableTiming));
+            PCR_CUDA(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
+        }
         PCR_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         PCR_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         use_aux = getenv("PRIMALCR_NO_AUX_STREAM") == nullptr;
@@ -151,8 +165,12 @@ struct Engine {
     ~Engine() {
         cudaSetDevice(cfg.device);      // the communicator stays in the process-wide cache
         if (aux) cudaStreamSynchronize(aux);
+        if (comm_stream) cudaStreamSynchronize(comm_stream);
         if (stream) cudaStreamSynchronize(stream);
         prof.resolve();
+        for (int q = 0; q < MAX_AR_GROUPS; ++q) if (ev_grp[q]) cudaEventDestroy(ev_grp[q]);
+        if (ev_comm) cudaEventDestroy(ev_comm);
+        if (comm_stream) cudaStreamDestroy(comm_stream);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         if (aux) cudaStreamDestroy(aux);
@@ -293,7 +311,8 @@ struct Engine {
             k_levels(ctx, X.rating, nnz, tab, T, X.level, bad);
             PCR_CUDA(cudaMemcpyAsync(h_counters, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
             sync();
-            PCR_REQUIRE(h_counters[0] == 0, "a rating rounds to a level that is not in the level table");
+            PCR_REQUIRE((h_counters[0] & 1) == 0, "a rating rounds to a level that is not in the level table");
+            ratings_integer = (h_counters[0] & 2) == 0;
         }
         lap("levels");
         // ---- size classes, heavy scratch
@@ -336,6 +355,22 @@ struct Engine {
         for (int q = 0; q < 3; ++q) { X.n_cls[q] = (int)cls[q].size(); X.cls_users[q] = upload_vec(cls[q]); }
         X.heavy_off = upload_vec(hoff); X.heavy_total = htot;
         X.heavy_begin = upload_vec(hb); X.heavy_end = upload_vec(he);
+        if (!cls[2].empty()) {            // work list of the heavy-user sort: the same chunks of 2048 ratings, any T
+            std::vector<i64> soff; std::vector<int32_t> scu, sclo;
+            i64 run = 0, maxlen = 0;
+            for (size_t q = 0; q < cls[2].size(); ++q) {
+                const i64 len = he[q] - hb[q];
+                soff.push_back(run); run += len; maxlen = std::max(maxlen, len);
+                for (i64 lo = 0; lo < len; lo += HEAVY_CHUNK) { scu.push_back((int32_t)q); sclo.push_back((int32_t)lo); }
+            }
+            hsort.n_users = (int)cls[2].size(); hsort.n_chunks = (int)scu.size();
+            hsort.max_passes = 0;
+            while (((i64)HEAVY_CHUNK << hsort.max_passes) < maxlen) ++hsort.max_passes;
+            hsort.begin = X.heavy_begin; hsort.end = X.heavy_end;
+            hsort.off = upload_vec(soff); hsort.chunk_user = upload_vec(scu); hsort.chunk_lo = upload_vec(sclo);
+            hsort.tmp_s = pool.alloc<double>((size_t)run); hsort.tmp_pos = pool.alloc<int32_t>((size_t)run);
+            sync();
+        }
         heavy_chunked = use_tiles && getenv("PRIMALCR_NO_LM") == nullptr && getenv("PRIMALCR_HEAVY_LEGACY") == nullptr && !cls[2].empty();
         if (heavy_chunked) {
             std::vector<i64> hoff_h; std::vector<int32_t> cu, clo, c0;
@@ -440,17 +475,50 @@ struct Engine {
             sync();
             pool.raw_free(bpos_d);
             std::vector<int32_t> cseg, cidx; std::vector<i64> cstart, cend, csup((size_t)d2 + 1, 0);
-            for (int blk = 0; blk < nb; ++blk)
-                for (i64 pcol = 0; pcol < d2; ++pcol) {
-                    const i64 lo = bpos[(size_t)pcol * (nb + 1) + blk], hi = blk + 1 == nb ? h_col[pcol + 1] : bpos[(size_t)pcol * (nb + 1) + blk + 1];
-                    // popular items get longer units so that no item has more than ~48 + nb partial sums to add up
-                    const i64 collen = h_col[pcol + 1] - h_col[pcol];
-                    const i64 chunk = std::max<i64>(ROWSUM_CHUNK, (collen + 47) / 48);
-                    for (i64 bb = lo; bb < hi; bb += chunk) {
-                        cseg.push_back((int32_t)pcol); cstart.push_back(bb); cend.push_back(std::min(bb + chunk, hi));
-                        csup[pcol + 1] += 1;
-                    }
+            // item groups for the pipelined all-reduce (one group when single-GPU): contiguous item ranges holding about
+            // the same number of ratings each
+            n_groups = 1;
+            if (world > 1) {
+                n_groups = getenv("PRIMALCR_AR_GROUPS") ? atoi(getenv("PRIMALCR_AR_GROUPS")) : 4;
+                n_groups = std::max(1, std::min<int>(std::min<i64>(n_groups, MAX_AR_GROUPS), d2));
+            }
+            grp_item0.assign((size_t)n_groups + 1, 0); grp_unit0.assign((size_t)n_groups + 1, 0);
+            if (n_groups > 1) {
+                // every rank must cut the items at the SAME places (the groups are all-reduced one by one): balance by the
+                // GLOBAL ratings per item = sum over ranks of this shard's column counts (exact in fp64)
+                std::vector<double> cnt((size_t)d2);
+                for (i64 pcol = 0; pcol < d2; ++pcol) cnt[pcol] = (double)(h_col[pcol + 1] - h_col[pcol]);
+                double *cnt_d = (double *)pool.raw_alloc(sizeof(double) * (size_t)d2);
+                PCR_CUDA(cudaMemcpyAsync(cnt_d, cnt.data(), sizeof(double) * (size_t)d2, cudaMemcpyHostToDevice, stream));
+                allreduce(cnt_d, (size_t)d2);
+                PCR_CUDA(cudaMemcpyAsync(cnt.data(), cnt_d, sizeof(double) * (size_t)d2, cudaMemcpyDeviceToHost, stream));
+                sync();
+                pool.raw_free(cnt_d);
+                double total = 0.0;
+                for (i64 pcol = 0; pcol < d2; ++pcol) total += cnt[pcol];
+                double run = 0.0; int gq = 1;
+                for (i64 pcol = 0; pcol < d2 && gq < n_groups; ++pcol) {
+                    run += cnt[pcol];
+                    while (gq < n_groups && run >= total * gq / n_groups) grp_item0[gq++] = pcol + 1;
                 }
+                for (; gq < n_groups; ++gq) grp_item0[gq] = d2;
+            }
+            grp_item0[n_groups] = d2;
+            for (int gq = 0; gq < n_groups; ++gq) {
+                grp_unit0[gq] = (i64)cseg.size();
+                for (int blk = 0; blk < nb; ++blk)
+                    for (i64 pcol = grp_item0[gq]; pcol < grp_item0[gq + 1]; ++pcol) {
+                        const i64 lo = bpos[(size_t)pcol * (nb + 1) + blk], hi = blk + 1 == nb ? h_col[pcol + 1] : bpos[(size_t)pcol * (nb + 1) + blk + 1];
+                        // popular items get longer units so that no item has more than ~48 + nb partial sums to add up
+                        const i64 collen = h_col[pcol + 1] - h_col[pcol];
+                        const i64 chunk = std::max<i64>(ROWSUM_CHUNK, (collen + 47) / 48);
+                        for (i64 bb = lo; bb < hi; bb += chunk) {
+                            cseg.push_back((int32_t)pcol); cstart.push_back(bb); cend.push_back(std::min(bb + chunk, hi));
+                            csup[pcol + 1] += 1;
+                        }
+                    }
+            }
+            grp_unit0[n_groups] = (i64)cseg.size();
             n_cunits = (i64)cseg.size();
             for (i64 pcol = 0; pcol < d2; ++pcol) csup[pcol + 1] += csup[pcol];
             cidx.resize(cseg.size());
@@ -475,8 +543,6 @@ struct Engine {
             meta.ulev = pool.alloc<uint16_t>((size_t)d1 * 8);
             PCR_CUDA(cudaMemsetAsync(meta.ulev, 0, sizeof(uint16_t) * (size_t)d1 * 8, stream));
         }
-        iota = pool.alloc<int32_t>((size_t)nnz);
-        k_iota32(ctx, iota, nnz);
         const size_t vn = (size_t)d2 * ld, un = (size_t)d1 * ld;
         U = pool.alloc<double>(un); V = pool.alloc<double>(vn);
         g = pool.alloc<double>(vn); delta = pool.alloc<double>(vn); rr = pool.alloc<double>(vn);
@@ -519,6 +585,7 @@ struct Engine {
     void ensure_eval_buffers(const DevCsr &C) {
         if (C.n_pt > ev_cap_pt) { ev_err_item = pool.alloc<i64>((size_t)C.n_pt); ev_cap_pt = C.n_pt; }
         if (C.d1 > ev_cap_d1 || ev_a == nullptr) {
+            ev_err_user = pool.alloc<i64>((size_t)C.d1);
             ev_a = pool.alloc<double>((size_t)C.d1); ev_b = pool.alloc<double>((size_t)C.d1);
             ev_c = pool.alloc<double>((size_t)C.d1); ev_d = pool.alloc<double>((size_t)C.d1); ev_cap_d1 = C.d1;
         }
@@ -586,11 +653,12 @@ struct Engine {
         return h_counters[which];
     }
     void zero_counters() { PCR_CUDA(cudaMemsetAsync(us.counters, 0, sizeof(int) * 4, stream)); }
-    void allreduce(double *buf, size_t n) {
+    void allreduce(double *buf, size_t n) { allreduce_on(stream, buf, n, "nccl_allreduce"); }
+    void allreduce_on(cudaStream_t st, double *buf, size_t n, const char *name) {
         if (world <= 1) return;
-        prof.begin("nccl_allreduce", stream, 0.0);
-        int r = g_nccl.AllReduce(buf, buf, n, PCR_NCCL_FLOAT64, PCR_NCCL_SUM, comm, stream);
-        prof.end(stream);
+        prof.begin(name, st, 0.0);
+        int r = g_nccl.AllReduce(buf, buf, n, PCR_NCCL_FLOAT64, PCR_NCCL_SUM, comm, st);
+        prof.end(st);
         if (r != 0) throw Error(PRIMALCR_ENCCL, std::string("ncclAllReduce failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
     }
     double pass_bytes(i64 n, i64 prows) const { return (double)n * (8.0 * k + 12.0) + 8.0 * k * (double)prows; }
@@ -611,7 +679,7 @@ struct Engine {
         Ctx &hc = par ? ctx_aux : ctx;
         if (par) fork_aux();
         if (X.n_cls[2] > 0) {
-            k_heavy_sort(hc, pool, &cub_tmp, &cub_tmp_bytes, sc, iota, meta.s, meta.pos, X.nnz, X.n_cls[2], X.heavy_begin, X.heavy_end);
+            k_heavy_sort(hc, hsort, sc, meta.s, meta.pos);
             k_gather_level(hc, X.cls_users[2], X.n_cls[2], nullptr, X.row_ptr, X.level, meta);
             if (heavy_chunked) k_heavy_prepare(hc, hv, meta, T);
         }
@@ -672,12 +740,28 @@ struct Engine {
         if (world <= 1) {
             k_rowsum(ctx, cu_seg, cu_start, cu_end, n_cunits, col_unit_ptr, col_unit_idx, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
                      cfg.lambda, x, out, 0, bytes, k);
-        } else {
-            k_rowsum(ctx, cu_seg, cu_start, cu_end, n_cunits, col_unit_ptr, col_unit_idx, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
-                     0.0, nullptr, out, 0, bytes, k);
-            allreduce(out, (size_t)d2 * ld);
-            k_axpby(ctx, out, 1.0, out, cfg.lambda, x, d2 * ld);
+            return;
         }
+        // Multi-GPU: this rank's partial sums, one item group at a time; as soon as a group's rows are final its all-reduce
+        // starts on the (high-priority) comm stream and runs beside the row sums of the next group.  Only the last
+        // group's collective is exposed.  lambda*x is added after the reduction (every rank holds the same x).
+        for (int gq = 0; gq < n_groups; ++gq) {
+            const i64 u0 = grp_unit0[gq], nu = grp_unit0[gq + 1] - u0, s0 = grp_item0[gq], ns = grp_item0[gq + 1] - s0;
+            if (ns <= 0) continue;
+            k_rowsum(ctx, cu_seg + u0, cu_start + u0, cu_end + u0, nu, col_unit_ptr + s0, col_unit_idx, ns, csc_user, csc2csr, cbuf, U, ld,
+                     nullptr, partial, 0.0, nullptr, out + (size_t)s0 * ld, 0, bytes * (double)nu / (double)std::max<i64>(n_cunits, 1), k, u0);
+            if (n_groups == 1) { allreduce(out, (size_t)d2 * ld); break; }
+            PCR_CUDA(cudaEventRecord(ev_grp[gq], stream));
+            PCR_CUDA(cudaStreamWaitEvent(comm_stream, ev_grp[gq], 0));
+            allreduce_on(comm_stream, out + (size_t)s0 * ld, (size_t)ns * ld, "nccl_allreduce_overlapped");
+        }
+        if (n_groups > 1) {
+            PCR_CUDA(cudaEventRecord(ev_comm, comm_stream));
+            prof.begin("nccl_exposed_wait", stream, 0.0);      // what the compute stream actually waits for the collectives
+            PCR_CUDA(cudaStreamWaitEvent(stream, ev_comm, 0));
+            prof.end(stream);
+        }
+        k_axpby(ctx, out, 1.0, out, cfg.lambda, x, d2 * ld);
     }
     // out[i] = lambda*x[i] + sum over user i of cbuf[e] * V[item(e)]   (U-side gradient / Hessian-vector product)
     void rowsum_users(const double *x, double *out, const uint8_t *active, int zero_if_empty) {
@@ -859,16 +943,31 @@ struct Engine {
     }
 
     // ------------------------------------------------------------------ compute_pairwise_error_ndcg util.cpp:434-542
-    void eval(int which, double *err, double *ndcg) {
+    // pair errors from the sorted state (O(len * T)) are possible for the training set of Primal-CR++ whenever the
+    // sorted state of the CURRENT scores exists and the ratings are integers (levels == exact ratings), T <= 8
+    bool eval_sorted_ok(int which) const {
+        return which == 0 && cfg.solver == 2 && scores_valid && meta_valid && ratings_integer && T <= 8 &&
+               getenv("PRIMALCR_EVAL_ALL_PAIRS") == nullptr;
+    }
+    // method: -1 automatic, 0 all-pairs kernel (the reference's O(len^2) loop util.cpp:467-479), 1 sorted-state count
+    void eval(int which, double *err, double *ndcg, int method = -1, i64 *err_user_host = nullptr) {
         require_ready();
         DevCsr &C = which == 0 ? X : XT;
         PCR_REQUIRE(which == 0 || has_test, "no test set loaded");
+        if (method == 1 && which == 0 && cfg.solver == 2 && ratings_integer && T <= 8) ensure_meta();
+        PCR_REQUIRE(method != 1 || eval_sorted_ok(which), "sorted-state evaluation needs the Primal-CR++ training set with integer ratings and <= 8 levels");
+        const bool sorted = method == 1 || (method < 0 && eval_sorted_ok(which));
         double *sc = which == 0 ? b : ev_score_t;
         if (which == 0 && scores_valid) sc = m;                      // m already holds U_i . V_j of the current factors
         else if (which == 0) train_dots(U, V, sc, nullptr);           // user-major units kernel (2x the generic one)
         else k_dots(ctx, U, C.user, V, C.item, C.nnz, ld, k, nullptr, sc, 0.0);
-        k_eval_pairs(ctx, C, sc, ev_err_item);
-        k_eval_users(ctx, C, sc, ev_err_item, cfg.ndcg_k, ev_a, ev_b, ev_c, ev_d);
+        if (sorted) k_eval_sorted(ctx, C, meta, T, ev_err_user);
+        else k_eval_pairs(ctx, C, sc, ev_err_item);
+        k_eval_users(ctx, C, sc, sorted ? ev_err_user : ev_err_item, sorted ? 1 : 0, cfg.ndcg_k, ev_a, ev_b, ev_c, ev_d);
+        if (err_user_host) {
+            if (!sorted) k_eval_item_to_user(ctx, C, ev_err_item, ev_err_user);
+            if (C.d1) PCR_CUDA(cudaMemcpyAsync(err_user_host, ev_err_user, sizeof(i64) * (size_t)C.d1, cudaMemcpyDeviceToHost, stream));
+        }
         k_sum(ctx, ev_a, C.d1, red_partials, slots + 0);
         k_sum(ctx, ev_b, C.d1, red_partials, slots + 1);
         k_sum(ctx, ev_c, C.d1, red_partials, slots + 2);
@@ -1074,6 +1173,17 @@ int primalcr_eval(primalcr_engine *e, int which, double *pairwise_error, double 
     CHECK_E(e) API_BEGIN
     double a = 0, b = 0;
     e->impl->eval(which, &a, &b);
+    e->impl->sync();
+    if (pairwise_error) *pairwise_error = a;
+    if (ndcg) *ndcg = b;
+    API_END
+}
+
+int primalcr_eval_error_counts(primalcr_engine *e, int which, int method, int64_t *err_per_user, double *pairwise_error, double *ndcg) {
+    CHECK_E(e) API_BEGIN
+    PCR_REQUIRE(method == 0 || method == 1, "method must be 0 (all pairs) or 1 (sorted state)");
+    double a = 0, b = 0;
+    e->impl->eval(which, &a, &b, method, (pcr::i64 *)err_per_user);
     e->impl->sync();
     if (pairwise_error) *pairwise_error = a;
     if (ndcg) *ndcg = b;

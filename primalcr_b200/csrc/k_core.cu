@@ -204,7 +204,25 @@ bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 
 
 // ------------------------------------------------------------------ K4: segmented weighted row sums
 
-template <int NCH>
+// L2 cache-policy loads (opt-in for the item-major pass, PRIMALCR_ROWSUM_L2HINT=1): the gathered U rows of the current user
+// block are asked to stay (evict_last), the ids / coefficients that stream through once are asked to leave first
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ double2 ldg_hint_d2(const double2 *p, unsigned long long pol) {
+    double2 v; asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ int ldg_hint_i32(const int32_t *p, unsigned long long pol) {
+    int v; asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ double ldg_hint_f64(const double *p, unsigned long long pol) {
+    double v; asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol)); return v;
+}
+
+template <int NCH, bool HINT = false>
 __global__ void __launch_bounds__(256, PCR_ROWSUM_MINB) rowsum_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
                                                      const i64 *__restrict__ un_end,
                                                      i64 n_units, unsigned long long *__restrict__ ticket,
@@ -213,6 +231,8 @@ __global__ void __launch_bounds__(256, PCR_ROWSUM_MINB) rowsum_kernel(const int3
                                                      const double *__restrict__ M, int ld, int nch,
                                                      const uint8_t *__restrict__ active, double *__restrict__ partial) {
     const int lane = threadIdx.x & 31;
+    unsigned long long pol_keep = 0, pol_stream = 0;
+    if (HINT) { pol_keep = l2_policy_evict_last(); pol_stream = l2_policy_evict_first(); }
     for (;;) {
         unsigned long long tk = 0;
         if (lane == 0) tk = atomicAdd(ticket, 1ull);     // units are consumed in list order (user-block-major for the CSC)
@@ -227,7 +247,10 @@ __global__ void __launch_bounds__(256, PCR_ROWSUM_MINB) rowsum_kernel(const int3
         for (i64 base = b; base < e; base += 32) {
             const i64 me = base + lane;
             int ri = 0; double wi = 0.0;
-            if (me < e) { ri = ridx[me]; wi = widx ? w[widx[me]] : w[me]; }
+            if (me < e) {
+                if (HINT) { ri = ldg_hint_i32(ridx + me, pol_stream); wi = ldg_hint_f64(w + ldg_hint_i32(widx + me, pol_stream), pol_stream); }
+                else { ri = ridx[me]; wi = widx ? w[widx[me]] : w[me]; }
+            }
             const int cnt = (e - base) < 32 ? (int)(e - base) : 32;
             // (measured: requesting the NEXT batch's ids / weights one batch ahead costs 8 registers and is slower: item-major
             //  pass 5.8 -> 6.3 ms, dots 4.23 -> 4.29 ms)
@@ -243,7 +266,7 @@ __global__ void __launch_bounds__(256, PCR_ROWSUM_MINB) rowsum_kernel(const int3
                 for (int q = 0; q < NCH; ++q) {
                     const int ci = lane + 32 * q;
                     if (ci < nch) {
-                        const double2 x = __ldg(row + ci);
+                        const double2 x = HINT ? ldg_hint_d2(row + ci, pol_keep) : __ldg(row + ci);
                         acc[q].x = fma(ww, x.x, acc[q].x);
                         acc[q].y = fma(ww, x.y, acc[q].y);
                     }
@@ -304,15 +327,19 @@ __global__ void __launch_bounds__(256) rowsum_finalize_kernel(const i64 *__restr
 void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_end, i64 n_units, const i64 *seg_unit_ptr,
               const int32_t *seg_unit_idx, i64 n_seg, const int32_t *ridx, const int32_t *widx, const double *w, const double *M, int ld,
               const uint8_t *active, double *partial, double lambda, const double *x, double *out,
-              int zero_if_empty, double bytes, int kk) {
+              int zero_if_empty, double bytes, int kk, i64 unit_base) {
     const int nch = (kk + 1) / 2;
+    double *partial_units = partial + (size_t)unit_base * ld;
     const int NCH = (nch + 31) / 32;
     PCR_REQUIRE(NCH <= 4, "rank too large for rowsum kernel (k <= 256)");
     const char *rs_name = widx ? "rowsum_items" : (active ? "rowsum_users_active" : "rowsum_users");
     if (n_units > 0) {
         PCR_CUDA(cudaMemsetAsync(c.ticket, 0, sizeof(unsigned long long), c.stream));
-#define RS(N) { const unsigned grid = resident_grid(rowsum_kernel<N>, 256, 0, c.sms, (n_units + 7) / 8); \
-                LAUNCH(c, rs_name, bytes, rowsum_kernel<N>, grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); }
+        static const bool l2hint = getenv("PRIMALCR_ROWSUM_L2HINT") != nullptr && atoi(getenv("PRIMALCR_ROWSUM_L2HINT")) != 0;
+#define RS(N) { if (l2hint && widx) { const unsigned grid = resident_grid(rowsum_kernel<N, true>, 256, 0, c.sms, (n_units + 7) / 8); \
+                  LAUNCH(c, rs_name, bytes, (rowsum_kernel<N, true>), grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial_units); } \
+                else { const unsigned grid = resident_grid(rowsum_kernel<N, false>, 256, 0, c.sms, (n_units + 7) / 8); \
+                  LAUNCH(c, rs_name, bytes, (rowsum_kernel<N, false>), grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial_units); } }
         switch (NCH) { case 1: RS(1) break; case 2: RS(2) break; case 3: RS(3) break; default: RS(4) break; }
 #undef RS
     }

@@ -173,12 +173,80 @@ void k_eval_pairs(Ctx &c, const DevCsr &X, const double *score, i64 *err_item) {
     LAUNCH(c, "eval_pairs", 0.0, eval_pairs_kernel, (unsigned)X.n_pt, 256, 0, X.pt_user, X.pt_j0, X.row_ptr, X.rating, score, err_item);
 }
 
+// The same integer from the SORTED state of Primal-CR++ in O(len * T) instead of O(len^2):
+//   errors_u = sum_b #{a : l_a < l_b and s_a >= s_b} = sum_b sum_{t < l_b} (C_t(n) - C_t(x_b)),
+// x_b = first sorted position whose score is >= s_b (the start of b's run of equal scores), C_t(x) = #{q < x : l_q = t}.
+// Valid when every rating is an integer (then the lround levels order the ratings exactly like the doubles the
+// reference compares, util.cpp:468-474) -- the engine checks that and otherwise keeps the all-pairs kernel above.
+// One warp per user walks the sorted positions 32 at a time: per-level ballots give the in-chunk prefix counts, two
+// small carried tables hold the counts before the chunk and at the start of a run of ties that began in an earlier chunk.
+template <int T>
+__global__ void __launch_bounds__(256) eval_sorted_kernel(const i64 *__restrict__ row_ptr, i64 d1, const double *__restrict__ s_sorted,
+                                                          const uint8_t *__restrict__ lev_sorted, i64 *__restrict__ err_user) {
+    const int lane = threadIdx.x & 31;
+    const i64 u = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (u >= d1) return;
+    const i64 start = row_ptr[u];
+    const int n = (int)(row_ptr[u + 1] - start);
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
+    int total[T], carry[T], run_cnt[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) { total[t] = 0; carry[t] = 0; run_cnt[t] = 0; }
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        const int lj = j < n ? (int)lev_sorted[start + j] : -1;
+#pragma unroll
+        for (int t = 0; t < T; ++t) total[t] += __popc(__ballot_sync(FULL, lj == t));
+    }
+    i64 err = 0;
+    double last_key = 0.0;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        const bool valid = j < n;
+        const double sj = valid ? s_sorted[start + j] : 0.0;
+        const int lj = valid ? (int)lev_sorted[start + j] : -1;
+        int excl[T];
+        unsigned bal[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) { bal[t] = __ballot_sync(FULL, lj == t); excl[t] = __popc(bal[t] & lt_mask); }
+        double sprev = __shfl_up_sync(FULL, sj, 1);
+        if (lane == 0) sprev = last_key;
+        const bool is_start = valid && (j == 0 || sprev != sj);        // double compare: -0.0 and +0.0 tie, as in `>=`
+        const unsigned sm = __ballot_sync(FULL, is_start) & le_mask;
+        const int sl = sm ? 31 - __clz(sm) : -1;                       // lane where my run of ties starts, -1: earlier chunk
+        int cs[T];
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int at = __shfl_sync(FULL, excl[t], sl & 31);
+            cs[t] = sl >= 0 ? carry[t] + at : run_cnt[t];
+        }
+        if (valid) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) if (t < lj) err += (i64)(total[t] - cs[t]);
+        }
+        const int cnt = (n - base) < 32 ? (n - base) : 32;
+#pragma unroll
+        for (int t = 0; t < T; ++t) { run_cnt[t] = __shfl_sync(FULL, cs[t], cnt - 1); carry[t] += __popc(bal[t]); }
+        last_key = __shfl_sync(FULL, sj, cnt - 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(FULL, err, o);
+    if (lane == 0) err_user[u] = err;
+}
+
+void k_eval_sorted(Ctx &c, const DevCsr &X, const SortedMeta &meta, int T, i64 *err_user) {
+    if (X.d1 <= 0) return;
+    const unsigned grid = (unsigned)((X.d1 + 7) / 8);
+    if (T <= 5) LAUNCH(c, "eval_sorted", 0.0, eval_sorted_kernel<5>, grid, 256, 0, X.row_ptr, X.d1, meta.s, meta.lev, err_user);
+    else        LAUNCH(c, "eval_sorted", 0.0, eval_sorted_kernel<8>, grid, 256, 0, X.row_ptr, X.d1, meta.s, meta.lev, err_user);
+}
+
 // per user: error ratio, NDCG@k (top-k by repeated arg-max; ties -> smaller index).  One WARP per user: the arg-max is a
 // shuffle reduction, no block barriers (the block-per-user version spent 60 __syncthreads per user: 11.5 ms for the
 // 480 k users of the Netflix shape, 7.5 ms even for a 10-ratings-per-user test set).
 __global__ void __launch_bounds__(256) eval_users_kernel(const i64 *__restrict__ row_ptr, const i64 *__restrict__ pt_ptr,
                                                          const double *__restrict__ rating, const double *__restrict__ score,
-                                                         const i64 *__restrict__ err_item, int ndcg_k, i64 d1,
+                                                         const i64 *__restrict__ err_item, int err_per_user, int ndcg_k, i64 d1,
                                                          double *__restrict__ err_ratio, double *__restrict__ ndcg,
                                                          double *__restrict__ has_pair, double *__restrict__ has_any) {
     __shared__ int sel_all[8][64];
@@ -194,7 +262,8 @@ __global__ void __launch_bounds__(256) eval_users_kernel(const i64 *__restrict__
     }
     if (lane == 0) {
         i64 err = 0;
-        for (i64 it = pt_ptr[u]; it < pt_ptr[u + 1]; ++it) err += err_item[it];
+        if (err_per_user) err = err_item[u];
+        else for (i64 it = pt_ptr[u]; it < pt_ptr[u + 1]; ++it) err += err_item[it];
         const i64 num = (i64)n * (n - 1) / 2;
         has_any[u] = 1.0;
         if (num != 0) { err_ratio[u] = (double)err / (double)num; has_pair[u] = 1.0; }
@@ -231,11 +300,25 @@ __global__ void __launch_bounds__(256) eval_users_kernel(const i64 *__restrict__
     if (lane == 0) ndcg[u] = dcg[0] / dcg[1];
 }
 
-void k_eval_users(Ctx &c, const DevCsr &X, const double *score, const i64 *err_item, int ndcg_k,
+void k_eval_users(Ctx &c, const DevCsr &X, const double *score, const i64 *err_item, int err_per_user, int ndcg_k,
                   double *err_ratio_user, double *ndcg_user, double *has_pair_user, double *has_any_user) {
     if (X.d1 <= 0) return;
     LAUNCH(c, "eval_users", 0.0, eval_users_kernel, (unsigned)((X.d1 + 7) / 8), 256, 0, X.row_ptr, X.pt_ptr, X.rating, score, err_item,
-           ndcg_k, X.d1, err_ratio_user, ndcg_user, has_pair_user, has_any_user);
+           err_per_user, ndcg_k, X.d1, err_ratio_user, ndcg_user, has_pair_user, has_any_user);
+}
+
+// per-user sums of the all-pairs work items (test entry point: integer counts per user)
+__global__ void __launch_bounds__(256) eval_item_to_user_kernel(const i64 *__restrict__ pt_ptr, i64 d1, const i64 *__restrict__ err_item,
+                                                                i64 *__restrict__ err_user) {
+    const i64 u = (i64)blockIdx.x * 256 + threadIdx.x;
+    if (u >= d1) return;
+    i64 err = 0;
+    for (i64 it = pt_ptr[u]; it < pt_ptr[u + 1]; ++it) err += err_item[it];
+    err_user[u] = err;
+}
+void k_eval_item_to_user(Ctx &c, const DevCsr &X, const i64 *err_item, i64 *err_user) {
+    if (X.d1 <= 0) return;
+    LAUNCH(c, "eval_item_to_user", 0.0, eval_item_to_user_kernel, (unsigned)((X.d1 + 255) / 256), 256, 0, X.pt_ptr, X.d1, err_item, err_user);
 }
 
 }  // namespace pcr

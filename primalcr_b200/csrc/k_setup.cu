@@ -42,7 +42,8 @@ __global__ void levels_kernel(const double *__restrict__ rating, i64 nnz, const 
         const i64 v = llround(rating[e]);
         int k = 0, hi = T;                      // the table is strictly ascending: lower bound
         while (k < hi) { const int mid = (k + hi) >> 1; if (table[mid] < v) k = mid + 1; else hi = mid; }
-        if (k == T || table[k] != v) { *bad = 1; k = 0; }
+        if (k == T || table[k] != v) { atomicOr(bad, 1); k = 0; }
+        if ((double)v != rating[e] && !(*reinterpret_cast<volatile int *>(bad) & 2)) atomicOr(bad, 2);
         out[e] = (uint8_t)k;
     }
 }
@@ -128,24 +129,6 @@ __global__ void csc_block_bounds_kernel(const i64 *__restrict__ col_ptr, const i
 void k_csc_block_bounds(Ctx &c, const i64 *col_ptr, const int32_t *csc_user, i64 d2, int nb, i64 block_users, i64 *bpos) {
     if (d2 <= 0) return;
     LAUNCH(c, "csc_block_bounds", 0.0, csc_block_bounds_kernel, grid_for(d2 * (nb + 1), 256, c.sms * 16), 256, 0, col_ptr, csc_user, d2, nb, block_users, bpos);
-}
-
-void k_heavy_sort(Ctx &c, DevPool &pool, void **temp, size_t *temp_bytes, const double *m, const int32_t *iota,
-                  double *s_sorted, int32_t *pos_sorted, i64 nnz, int n_heavy, const i64 *begin, const i64 *end) {
-    if (n_heavy <= 0) return;
-    size_t need = 0;
-    PCR_CUDA(cub::DeviceSegmentedSort::StableSortPairs(nullptr, need, m, s_sorted, iota, pos_sorted, nnz, (i64)n_heavy,
-                                                       begin, end, c.stream));
-    if (need > *temp_bytes) {
-        *temp = pool.alloc<unsigned char>(need);      // grows monotonically; freed with the engine
-        *temp_bytes = need;
-        // the pool allocates in the order of ITS stream; this sort may run on the side stream
-        if (pool.async && pool.stream != c.stream) PCR_CUDA(cudaStreamSynchronize(pool.stream));
-    }
-    c.prof->begin("heavy_sort(cub)", c.stream, 0.0);
-    PCR_CUDA(cub::DeviceSegmentedSort::StableSortPairs(*temp, need, m, s_sorted, iota, pos_sorted, nnz, (i64)n_heavy,
-                                                       begin, end, c.stream));
-    c.prof->end(c.stream);
 }
 
 }  // namespace pcr

@@ -13,6 +13,7 @@ struct Ctx {               // what every launcher needs
 
 // ---------------------------------------------------------------- k_setup.cu (one-time preprocessing)
 void k_expand_users(Ctx &c, const i64 *row_ptr, i64 d1, i64 nnz, int32_t *user_out);
+// *bad_flag |= 1: a rating rounds to a value outside the table; |= 2: some rating is not an integer
 void k_levels(Ctx &c, const double *rating, i64 nnz, const i64 *table_dev, int T, uint8_t *level_out, int *bad_flag);
 void k_iota32(Ctx &c, int32_t *out, i64 n);
 void k_check_range(Ctx &c, const int32_t *idx, i64 n, i64 bound, int *bad_flag);   // *bad_flag |= 1 if any idx outside [0, bound)
@@ -21,9 +22,10 @@ void k_csc_block_bounds(Ctx &c, const i64 *col_ptr, const int32_t *csc_user, i64
 // CSC (by item) of a CSR: col_ptr[d2+1], csc2csr[nnz] (stable: users ascending inside an item), csc_user[nnz]
 void k_build_csc(Ctx &c, DevPool &pool, const int32_t *item, const int32_t *user, i64 nnz, i64 d2,
                  i64 *col_ptr, int32_t *csc2csr, int32_t *csc_user);
-// heavy users: stable segmented sort of (score, position) pairs with CUB; temp storage grows inside `pool`
-void k_heavy_sort(Ctx &c, DevPool &pool, void **temp, size_t *temp_bytes, const double *m, const int32_t *iota,
-                  double *s_sorted, int32_t *pos_sorted, i64 nnz, int n_heavy, const i64 *begin, const i64 *end);
+
+// ---------------------------------------------------------------- k_hsort.cu
+// heavy users: segmented sort of (score, position) pairs -- chunk sort in shared memory + merge-path passes over chunks
+void k_heavy_sort(Ctx &c, const HeavySortPlan &h, const double *m, double *s_sorted, int32_t *pos_sorted);
 
 // ---------------------------------------------------------------- k_core.cu
 // out[e] = P[prow[e]] . Q[qrow[e]]  (rows are ld-strided, ld % 4 == 0); skipped when active[prow[e]] == 0
@@ -37,7 +39,9 @@ bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 
 void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_end, i64 n_units, const i64 *seg_unit_ptr,
               const int32_t *seg_unit_idx, i64 n_seg, const int32_t *ridx, const int32_t *widx, const double *w, const double *M, int ld,
               const uint8_t *active, double *partial, double lambda, const double *x, double *out,
-              int zero_if_empty, double bytes, int kk);
+              int zero_if_empty, double bytes, int kk, i64 unit_base = 0);
+// unit_base: the unit arrays passed in are a slice starting at global unit `unit_base` (seg_unit_idx holds GLOBAL unit ids and
+// `partial` is the global base): used to run the item-major pass one item group at a time (multi-GPU pipelining)
 // per-user sort of scores (classes S and L, bitonic in shared memory); writes s / pos / lev
 void k_sort_users(Ctx &c, int cls, const int32_t *users, int n_users, const uint8_t *active, const i64 *row_ptr,
                   const double *m, const uint8_t *level, SortedMeta &meta);
@@ -109,7 +113,11 @@ void k_pair_obj_users(Ctx &c, const DevCsr &X, const uint8_t *active, const doub
 void k_has_pairs(Ctx &c, const DevCsr &X, uint8_t *has_pairs);
 // evaluation: pair errors per work item -> per user ratio; ndcg per user
 void k_eval_pairs(Ctx &c, const DevCsr &X, const double *score, i64 *err_item);
-void k_eval_users(Ctx &c, const DevCsr &X, const double *score, const i64 *err_item, int ndcg_k,
+// the same integer per USER from the sorted state (O(len * T), integer ratings only; T <= 8)
+void k_eval_sorted(Ctx &c, const DevCsr &X, const SortedMeta &meta, int T, i64 *err_user);
+void k_eval_item_to_user(Ctx &c, const DevCsr &X, const i64 *err_item, i64 *err_user);
+// err_per_user != 0: err_item holds one count per user (k_eval_sorted) instead of one per pair work item
+void k_eval_users(Ctx &c, const DevCsr &X, const double *score, const i64 *err_item, int err_per_user, int ndcg_k,
                   double *err_ratio_user, double *ndcg_user, double *has_pair_user, double *has_any_user);
 
 }  // namespace pcr

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
 #include <iostream>
 #include <thread>
@@ -25,13 +26,39 @@ inline void die(const char *what, int rc) {
 
 inline void log_line(const char *line, void *) { std::cout << line << std::endl; }
 
-// find_levels pcrpp.cpp:38-49 as ONE global ascending table of distinct lround(rating)
+// wall-clock laps of the host side, printed to stderr when PRIMALCR_VERBOSE_SETUP is set
+struct Lap {
+    bool on; std::chrono::steady_clock::time_point t;
+    Lap() : on(getenv("PRIMALCR_VERBOSE_SETUP") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void operator()(const char *what) {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[primalcr host] %-32s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
+// find_levels pcrpp.cpp:38-49 as ONE global ascending table of distinct lround(rating).  One pass over the ratings on all
+// host threads (each keeps its own small sorted table, merged at the end): 100 M ratings take ~0.1 s instead of ~1 s.
 inline std::vector<int64_t> global_levels(const FlatCsr &X) {
     std::vector<int64_t> lv;
-    for (int64_t e = 0; e < X.nnz; ++e) {
-        const int64_t l = llround(X.rating[e]);
-        auto it = std::lower_bound(lv.begin(), lv.end(), l);
-        if (it == lv.end() || *it != l) lv.insert(it, l);
+#pragma omp parallel
+    {
+        std::vector<int64_t> mine;
+        int64_t last = 0; bool have_last = false;
+#pragma omp for schedule(static) nowait
+        for (int64_t e = 0; e < X.nnz; ++e) {
+            const int64_t l = llround(X.rating[e]);
+            if (have_last && l == last) continue;
+            last = l; have_last = true;
+            auto it = std::lower_bound(mine.begin(), mine.end(), l);
+            if (it == mine.end() || *it != l) mine.insert(it, l);
+        }
+#pragma omp critical
+        for (int64_t l : mine) {
+            auto it = std::lower_bound(lv.begin(), lv.end(), l);
+            if (it == lv.end() || *it != l) lv.insert(it, l);
+        }
     }
     if (lv.empty()) lv.push_back(0);
     return lv;
@@ -46,6 +73,7 @@ inline int gpus_from_env() {
 // U (d1 x k) and V (d2 x k) row-major, updated in place -- like the reference's mat_t& U, mat_t& V
 inline void solve(const primalcr_config &base, const FlatCsr &X, const FlatCsr &XT, double *U, double *V, int gpus) {
     const int k = base.k;
+    Lap lap;
     // Primal-CR (-s 1) compares the exact ratings (pcr.cpp:23): no level table, any rating scale
     const std::vector<int64_t> levels = base.solver == PRIMALCR_SOLVER_PCRPP ? global_levels(X) : std::vector<int64_t>();
     std::vector<int64_t> bounds(gpus + 1, 0);            // contiguous user shards balanced by nnz
@@ -55,13 +83,16 @@ inline void solve(const primalcr_config &base, const FlatCsr &X, const FlatCsr &
         bounds[r] = std::min<int64_t>(std::max(bounds[r], bounds[r - 1]), X.d1);
     }
     bounds[gpus] = X.d1;
+    lap("level table + shard bounds");
     char uid[128] = {0};
     if (gpus > 1) PCRHOST_CK(primalcr_nccl_unique_id(uid));
     auto worker = [&](int rank) {
         primalcr_config cfg = base;
         cfg.device = rank;
         primalcr_engine *e = nullptr;
+        Lap wl;
         PCRHOST_CK(primalcr_create(&e, &cfg));
+        if (rank == 0) wl("create engine (CUDA context)");
         if (!levels.empty()) PCRHOST_CK(primalcr_set_levels(e, levels.data(), (int)levels.size()));
         PCRHOST_CK(primalcr_comm_init(e, rank, gpus, gpus > 1 ? uid : nullptr));
         const int64_t u0 = bounds[rank], u1 = bounds[rank + 1];
@@ -78,10 +109,15 @@ inline void solve(const primalcr_config &base, const FlatCsr &X, const FlatCsr &
             const int64_t bt = shard(XT, rpt);
             PCRHOST_CK(primalcr_set_test_csr(e, rpt.back(), rpt.data(), XT.item + bt, XT.rating + bt));
         }
+        if (rank == 0) wl("comm init + set_train/test");
         PCRHOST_CK(primalcr_set_factors(e, U + (size_t)u0 * k, V));
+        if (rank == 0) wl("set_factors");
         PCRHOST_CK(primalcr_run(e, log_line, nullptr));
+        if (rank == 0) wl("run (all iterations)");
         PCRHOST_CK(primalcr_get_factors(e, U + (size_t)u0 * k, rank == 0 ? V : nullptr));
+        if (rank == 0) wl("get_factors");
         primalcr_destroy(e);
+        if (rank == 0) wl("destroy engine");
     };
     if (gpus == 1) worker(0);
     else {

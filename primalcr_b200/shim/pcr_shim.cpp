@@ -20,19 +20,22 @@ namespace {
 
 std::vector<double> flatten(const mat_t &M, int k) {
     std::vector<double> out(M.size() * (size_t)k);
-    for (size_t i = 0; i < M.size(); ++i) for (int j = 0; j < k; ++j) out[i * k + j] = M[i][j];
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)M.size(); ++i) for (int j = 0; j < k; ++j) out[(size_t)i * k + j] = M[i][j];
     return out;
 }
 
 void solve(int solver, smat_t &R, mat_t &U, mat_t &V, testset_t &T, parameter &param) {
+    pcrhost::Lap lap;
     const int k = param.k;
-    // training set: smat_t's row-major arrays (util.h:157-271): row_ptr / col_idx / val_t, items ascending per row
+    // training set: smat_t's row-major arrays (util.h:157-271): row_ptr (long) / col_idx (unsigned) / val_t (double), items
+    // ascending per row.  They already ARE a CSR with 64-bit offsets, 32-bit ids and fp64 values: handed to the C ABI in
+    // place, no copies (ids are < 2^31: the loader reads them with %d, util.h:126).
     const long d1 = R.rows, d2 = R.cols, nnz = R.nnz;
-    std::vector<int64_t> row_ptr(R.row_ptr, R.row_ptr + d1 + 1);
-    std::vector<int32_t> item((size_t)nnz);
-    std::vector<double> rating(R.val_t, R.val_t + nnz);
-    for (long e = 0; e < nnz; ++e) item[e] = (int32_t)R.col_idx[e];
-    R.clear_space();                                   // the reference's convert() frees X too (util.cpp:244)
+    static_assert(sizeof(long) == sizeof(int64_t) && sizeof(unsigned) == sizeof(int32_t), "LP64 expected");
+    const int64_t *row_ptr = reinterpret_cast<const int64_t *>(R.row_ptr);
+    const int32_t *item = reinterpret_cast<const int32_t *>(R.col_idx);
+    const double *rating = R.val_t;
     // test set: convert(testset_t&, d1, d2) util.cpp:250-274, literally (entries are taken in file order)
     std::vector<int64_t> rpt((size_t)d1 + 1, 0);
     std::vector<int32_t> itt((size_t)T.nnz);
@@ -47,15 +50,21 @@ void solve(int solver, smat_t &R, mat_t &U, mat_t &V, testset_t &T, parameter &p
     }
     rpt[d1] = cc;
     std::vector<double> Uf = flatten(U, k), Vf = flatten(V, k);
+    lap("shim: flatten test set, U, V");
     primalcr_config cfg; primalcr_default_config(&cfg);
     cfg.solver = solver; cfg.k = k; cfg.lambda = param.lambda; cfg.stepsize = param.stepsize;
     cfg.maxiter = param.maxiter; cfg.ndcg_k = param.ndcg_k; cfg.do_predict = param.do_predict;
     cfg.threads = param.threads;
-    pcrhost::FlatCsr fx{d1, d2, nnz, row_ptr.data(), item.data(), rating.data()};
+    pcrhost::FlatCsr fx{d1, d2, nnz, row_ptr, item, rating};
     pcrhost::FlatCsr ft{d1, d2, cc, rpt.data(), itt.data(), rat.data()};
     pcrhost::solve(cfg, fx, ft, Uf.data(), Vf.data(), pcrhost::gpus_from_env());
-    for (size_t i = 0; i < U.size(); ++i) for (int j = 0; j < k; ++j) U[i][j] = Uf[i * k + j];
-    for (size_t i = 0; i < V.size(); ++i) for (int j = 0; j < k; ++j) V[i][j] = Vf[i * k + j];
+    lap("shim: solve (see host laps)");
+    R.clear_space();                                   // the reference's convert() frees X too (util.cpp:244)
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)U.size(); ++i) for (int j = 0; j < k; ++j) U[i][j] = Uf[(size_t)i * k + j];
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)V.size(); ++i) for (int j = 0; j < k; ++j) V[i][j] = Vf[(size_t)i * k + j];
+    lap("shim: copy U, V back into mat_t");
 }
 
 }  // namespace

@@ -9,8 +9,9 @@ Cases (data sets come from the committed deterministic generator, CPU stream; th
                Primal-CR++ k=200 lambda=5000, 2 outer iterations, evaluation on
   ml1m_pcr     ml1m-shape (6040 x 3952, 939,809 ratings), Primal-CR (-s 1) k=100 lambda=5000, 2 outer iterations
 Each fixture holds, from the single-threaded C restatement (bit-identical to `omp-pmf-train -n 1`, tests/test_oracle.py):
-objective per iteration, the 8 control-flow counters per iteration, error / NDCG@10 per iteration, sampled rows and
-column sums of the final U and V; and from the UNMODIFIED reference (race-free objects, all host threads) the same
+objective per iteration, the 8 control-flow counters per iteration, error / NDCG@10 per iteration, the integer pair-error
+count of every user (training and test set) and the users whose row has collapsed to rounding noise after every
+iteration, sampled rows and column sums of the final U and V; and from the UNMODIFIED reference (race-free objects, all host threads) the same
 objectives and evaluation numbers, so the fixture itself shows oracle == reference at this size.
 """
 import hashlib
@@ -64,9 +65,31 @@ def make(name):
     assert R is not None, "build oracle/_ref first (make -C oracle ref)"
     ref = R.train(solver, X, XT, U0, V0, lam, iters, do_predict=c["predict"], threads=os.cpu_count() or 1)
     print(name, "reference (race-free, %d threads) %.0fs obj %s" % (os.cpu_count(), time.time() - t, ref["obj"]), flush=True)
+    # single-threaded C restatement, ONE outer iteration per call so that the state after every iteration is visible:
+    # objective, counters, evaluation incl. the integer pair-error count of every user, and the set of users whose row
+    # collapsed to rounding noise (zero loss gradient => the Newton step returns u_i - u_i; the ORDER of such a user's
+    # ~1e-17 scores, hence its evaluation, is noise in the reference too -- the GPU test masks exactly these users)
     t = time.time()
-    orc = ob.oracle().train(solver, X, XT, U0, V0, lam, iters, do_predict=c["predict"])
-    print(name, "oracle (1 thread) %.0fs obj %s" % (time.time() - t, orc["obj"]), flush=True)
+    O = ob.oracle()
+    U, V = U0, V0
+    objs, counters, evals, err_train, err_test, collapsed = [], [], [], [], [], []
+
+    def evaluate(U, V):
+        row = []
+        for Xs, store in ((X, err_train), (XT, err_test)):
+            out, _, per_user = O.eval(Xs, U, V, 10, want_counts=True)
+            row += [out[0], out[1]]; store.append(per_user.copy())
+        evals.append(row); collapsed.append(np.abs(U).max(1) < 1e-9)
+
+    for it in range(iters + 1):
+        res = O.train(solver, X, None, U, V, lam, 1 if it else 0, do_predict=0)
+        if it == 0:
+            objs.append(res["obj"][0])
+        else:
+            objs.append(res["obj"][1]); counters.append(res["counters"][0]); U, V = res["U"], res["V"]
+        evaluate(U, V)
+        print(name, "oracle iteration %d: obj %.12g, %d collapsed users (%.0fs)" % (it, objs[-1], collapsed[-1].sum(), time.time() - t), flush=True)
+    orc = dict(obj=np.array(objs), counters=np.array(counters), evals=np.array(evals), U=U, V=V)
     rel = np.abs(orc["obj"] - ref["obj"]) / np.abs(ref["obj"])
     print(name, "oracle vs reference: objective rel err", rel, "evals abs err", np.abs(orc["evals"] - ref["evals"]).max(),
           "U", np.abs(orc["U"] - ref["U"]).max() / np.abs(ref["U"]).max(), "V", np.abs(orc["V"] - ref["V"]).max() / np.abs(ref["V"]).max(),
@@ -80,6 +103,7 @@ def make(name):
                d1=ds.d1, d2=ds.d2, nnz=ds.train.nnz, nnz_test=ds.test.nnz, digest=dataset_digest(ds),
                obj=orc["obj"], evals=orc["evals"], counters=orc["counters"],
                ref_obj=ref["obj"], ref_evals=ref["evals"], ref_threads=os.cpu_count() or 1,
+               err_train=np.array(err_train), err_test=np.array(err_test), collapsed=np.packbits(np.array(collapsed), axis=1),
                urows=urows, vrows=vrows)
     for tag, res in (("", orc), ("ref_", ref)):
         for nm, M, rows in (("U", res["U"], urows), ("V", res["V"], vrows)):

@@ -151,6 +151,38 @@ def test_eval(name, which):
     e.close()
 
 
+@pytest.mark.parametrize("name", ["tiny", "ragged", "ragged_real"])
+def test_eval_pair_counts_sorted_vs_all_pairs(name):
+    """The O(len * levels) pair-error count from the Primal-CR++ sorted state is the SAME integer, user by
+    user, as the all-pairs kernel and as the reference's O(len^2) loop (util.cpp:467-479) -- with exact score ties
+    (duplicated item rows, an all-zero user row: `>=` counts ties as errors) and a heavy user of 5000 ratings.  With
+    real-valued ratings lround levels do not order the ratings, so the sorted path must refuse and the exact-double
+    all-pairs count stays in charge."""
+    ds = dataset(name)
+    k = 5
+    U, V = np_init(ds.d1, ds.d2, k, seed=13, scale=0.7)
+    rp = ds.train.row_ptr
+    big = int(np.argmax(np.diff(rp)))
+    its = ds.train.item[rp[big]:rp[big + 1]]
+    V[its[1::7]] = V[its[0]]                      # many exactly equal scores inside the heaviest user (and others)
+    U[min(10, ds.d1 - 1)] = 0.0                   # a user whose scores all tie at 0
+    e, _, _ = make_engine(ds, k, 10.0, U=U, V=V, levels=(name != "ragged_real"))
+    want, counts, per_user = ob.oracle().eval(to_csr(ds.train), U, V, 10, want_counts=True)
+    err0, ndcg0, c0 = e.eval_error_counts(0, method=0)
+    assert np.array_equal(c0, per_user)
+    assert abs(err0 - want[0]) < 1e-12 and abs(ndcg0 - want[1]) < 1e-12
+    if name == "ragged_real":
+        with pytest.raises(api.PrimalCRError, match="integer ratings"):
+            e.eval_error_counts(0, method=1)
+    else:
+        err1, ndcg1, c1 = e.eval_error_counts(0, method=1)
+        assert np.array_equal(c1, per_user)
+        assert err1 == err0 and ndcg1 == ndcg0
+        e.initial_objective()                      # sorted state now exists: plain eval() takes the sorted path by itself
+        assert e.eval(0) == (err0, ndcg0)
+    e.close()
+
+
 @pytest.mark.parametrize("solver", [2, 1])
 @pytest.mark.parametrize("name,k,lam", [("tiny", 7, 50.0), ("ragged", 10, 20.0), ("tiny", 100, 5000.0)])
 def test_update_V_then_U(name, k, lam, solver):

@@ -35,40 +35,93 @@ def _digest(ds):
     return h.hexdigest()
 
 
-@pytest.mark.parametrize("case", ["netflix005", "powerlaw001", "ml1m_pcr"])
-def test_scale_parity_against_the_reference(case):
+def _load(case):
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_%s.npz" % case))
     ds = synth_dataset(str(g["shape"]), scale=float(g["scale"]), device="cpu")
     assert _digest(ds) == str(g["digest"]), "the synthetic generator no longer reproduces the fixture's data set"
+    return g, ds
+
+
+@pytest.mark.parametrize("case", ["netflix005", "powerlaw001", "ml1m_pcr"])
+def test_scale_parity_against_the_reference(case):
+    g, ds = _load(case)
     k, lam, iters, solver = int(g["k"]), float(g["lam"]), int(g["iters"]), int(g["solver"])
     U0 = api.reference_init(ds.d1, k); V0 = api.reference_init(ds.d2, k)
     e = api.Engine(api.Parameter(solver_type=solver, k=k, lambda_=lam, maxiter=iters))
     e.set_train(ds.train); e.set_test(ds.test); e.set_factors(U0, V0)
+    # How well two runs of the REFERENCE agree with each other (single-threaded restatement vs the all-threads race-free
+    # build: only the order of its `omp atomic` adds differs).  On the power-law shape (one 99,990-rating user, k=200) the
+    # truncated CG amplifies those last-bit differences to ~7e-7 of the objective by iteration 2 -- the reference cannot
+    # reproduce itself better than that, so the GPU is held to max(1e-9, 3 x that spread) there and to 1e-9 elsewhere.
+    spread = np.abs(g["obj"] - g["ref_obj"]) / np.abs(g["obj"])
+    collapsed = np.unpackbits(g["collapsed"], axis=1)[:, :ds.d1].astype(bool)
+    lens, lens_t = ds.train.lens(), ds.test.lens()
 
-    def check_eval(i):
-        for which, c0 in ((0, 0), (1, 2)):
-            err, ndcg = e.eval(which)
-            for ev in (g["evals"], g["ref_evals"]):
-                assert abs(err - ev[i, c0]) < ERR_TOL, (i, which, err, ev[i, c0])
-                assert abs(ndcg - ev[i, c0 + 1]) < NDCG_TOL, (i, which, ndcg, ev[i, c0 + 1])
+    def check_eval(i, U):
+        # users whose row is rounding noise (|u_i| < 1e-9: zero loss gradient, the Newton step returned u_i - u_i) have
+        # noise for scores, in the reference too: the SET of such users must match, everybody else's integer pair-error
+        # count must be identical, and the means (which include the noise users) agree to what those users can move
+        if U is not None:
+            assert np.array_equal(np.abs(U).max(1) < 1e-9, collapsed[i]), i
+        ok = ~collapsed[i]
+        for which, c0, want_cnt, ln in ((0, 0, g["err_train"][i], lens), (1, 2, g["err_test"][i], lens_t)):
+            err, ndcg, cnt = e.eval_error_counts(which, method=0)
+            assert np.array_equal(cnt[ok], want_cnt[ok]), (i, which, int((cnt[ok] != want_cnt[ok]).sum()))
+            if which == 0 and solver == 2:          # the O(len * levels) count from the sorted state: same integers
+                err1, ndcg1, cnt1 = e.eval_error_counts(0, method=1)
+                assert np.array_equal(cnt1, cnt) and err1 == err and ndcg1 == ndcg
+            noise = float(((ln >= 2) & collapsed[i]).sum()) / max(int((ln >= 2).sum()), 1)     # each such user moves the mean by <= 1/n
+            assert abs(err - g["evals"][i, c0]) <= ERR_TOL + noise, (i, which, err, g["evals"][i, c0])
+            assert abs(ndcg - g["evals"][i, c0 + 1]) < NDCG_TOL + noise, (i, which, ndcg, g["evals"][i, c0 + 1])
 
     o = e.initial_objective()
     assert abs(o - g["obj"][0]) <= 1e-11 * abs(g["obj"][0])
-    check_eval(0)
+    check_eval(0, U0)
     for i in range(1, iters + 1):
         o = e.outer_iteration()
         c = e.counters(); want = [int(x) for x in g["counters"][i - 1]]
         got = [c[n] for n in ("v_cg_iters", "v_ls_trials", "v_ls_accepted", "u_cg_len_sum", "u_ls_len_sum", "u_skipped",
                               "u_cg_iters", "u_ls_trials")]
         assert got == want, (i, got, want)                 # every branch of the truncated CG / line searches / skip tests
-        assert abs(o - g["obj"][i]) <= OBJ_TOL * abs(g["obj"][i]), (i, o, g["obj"][i])
-        assert abs(o - g["ref_obj"][i]) <= OBJ_TOL * abs(g["ref_obj"][i]), (i, o, g["ref_obj"][i])
-        check_eval(i)
-    U, V = e.get_factors()
+        tol = max(OBJ_TOL, 3 * spread[i])
+        assert abs(o - g["obj"][i]) <= tol * abs(g["obj"][i]), (i, o, g["obj"][i])
+        assert abs(o - g["ref_obj"][i]) <= tol * abs(g["ref_obj"][i]), (i, o, g["ref_obj"][i])
+        U, V = e.get_factors()
+        check_eval(i, U)
     e.close()
-    for tag in ("", "ref_"):
-        for M, nm, rows in ((U, "U", g["urows"]), (V, "V", g["vrows"])):
-            scale = float(g[tag + nm + "_absmax"])
-            assert np.abs(M[rows] - g[tag + nm + "_rows"]).max() <= 1e-8 * scale, (tag, nm)
-            assert np.abs(M.sum(0) - g[tag + nm + "_colsum"]).max() <= 1e-8 * scale * np.sqrt(M.shape[0]), (tag, nm)
-            assert abs(float((M * M).sum()) - float(g[tag + nm + "_sq"])) <= 1e-9 * float(g[tag + nm + "_sq"]), (tag, nm)
+    vec_tol = max(1e-8, 1e3 * spread.max())      # the factors move ~1e3 x more than the objective under the same perturbation
+    for M, nm, rows in ((U, "U", g["urows"]), (V, "V", g["vrows"])):
+        scale = float(g[nm + "_absmax"])
+        assert np.abs(M[rows] - g[nm + "_rows"]).max() <= vec_tol * scale, nm
+        assert np.abs(M.sum(0) - g[nm + "_colsum"]).max() <= vec_tol * scale * np.sqrt(M.shape[0]), nm
+        assert abs(float((M * M).sum()) - float(g[nm + "_sq"])) <= max(1e-9, 10 * spread.max()) * float(g[nm + "_sq"]), nm
+
+
+@pytest.mark.parametrize("gpus", [2, 4, 8])
+def test_scale_parity_sharded_over_gpus(tmp_path, gpus):
+    """The same Netflix-shape x 0.05 fixture through the C++ host driver with the users sharded over 2 / 4 / 8 GPUs (one
+    engine per GPU, item-group pipelined all-reduce of the V-side sums): printed objectives (6 digits) and the model file
+    against the reference's trajectory.  Each rank owns different items' ratings, so this is the test that sees a rank
+    reducing the wrong rows."""
+    import subprocess
+    import torch
+    from primalcr_b200.data import Dataset, Ratings, load_model, write_reference_dir
+    if torch.cuda.device_count() < gpus:
+        pytest.skip("needs %d GPUs" % gpus)
+    g, ds = _load("netflix005")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "primalcr_b200", "bin", "primalcr-train")
+    write_reference_dir(str(tmp_path / "data"), Dataset(ds.train, Ratings.empty(ds.d1, ds.d2)))
+    k, lam, iters = int(g["k"]), float(g["lam"]), int(g["iters"])
+    env = dict(os.environ, PRIMALCR_GPUS=str(gpus), PRIMALCR_NO_TEXT_DUMP="1")
+    out = subprocess.run([exe, "-s", "2", "-k", str(k), "-l", str(lam), "-t", str(iters), "-p", "0", "-n", "8",
+                          str(tmp_path / "data"), str(tmp_path / "model")], cwd=tmp_path, capture_output=True, text=True,
+                         env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    objs = np.array([float(l.split()[-1]) for l in out.stdout.splitlines() if l.startswith("Iter ")])
+    assert len(objs) == iters + 1 and np.all(np.abs(objs - g["obj"]) <= 2e-5 * np.abs(g["obj"]))
+    U, V = load_model(str(tmp_path / "model"))
+    for M, nm, rows in ((U, "U", g["urows"]), (V, "V", g["vrows"])):
+        scale = float(g[nm + "_absmax"])
+        assert np.abs(M[rows] - g[nm + "_rows"]).max() <= 1e-8 * scale, nm
+        assert abs(float((M * M).sum()) - float(g[nm + "_sq"])) <= 1e-9 * float(g[nm + "_sq"]), nm
