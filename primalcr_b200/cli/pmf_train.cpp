@@ -114,9 +114,11 @@ int main(int argc, char **argv) {
 #ifdef _OPENMP
     omp_set_num_threads(threads > 0 ? threads : 1);
 #endif
+    pcrhost::Lap lap;                 // PRIMALCR_VERBOSE_SETUP=1: wall-time split load / init / solve / write on stderr
     pcrhost::DataDir data;
     try { data = pcrhost::load_dir(input); }
     catch (const std::exception &ex) { fprintf(stderr, "primalcr-train: %s\n", ex.what()); fclose(model_fp); remove(model_tmp.c_str()); return 1; }
+    lap("cli: load data directory");
     const pcrhost::Csr &X = data.train, &T = data.test;
     const int k = cfg.k;
     std::vector<double> U((size_t)X.d1 * k), V((size_t)X.d2 * k);
@@ -133,6 +135,7 @@ int main(int argc, char **argv) {
         }
         fclose(wf);
     }
+    lap("cli: initial U, V");
     std::cout << "the rank is " << k << std::endl;
     std::cout << "the number of rows is " << X.d1 << " and the number of cols is " << X.d2 << std::endl;
     if (cfg.solver == PRIMALCR_SOLVER_PCR) std::cout << "nnz: " << X.nnz << std::endl;      // pmf-train.cpp:201
@@ -142,17 +145,20 @@ int main(int argc, char **argv) {
     pcrhost::FlatCsr ft{T.d1, T.d2, T.nnz, T.row_ptr.data(), T.item.data(), T.rating.data()};
     pcrhost::solve(cfg, fx, ft, U.data(), V.data(), pcrhost::gpus_from_env());
     printf("Wall-time: %lg secs\n", wall() - t0);
+    lap("cli: solve (see host laps)");
     const bool pp = cfg.solver == PRIMALCR_SOLVER_PCRPP;
     const std::string suffix = pp ? "" : std::to_string((int)cfg.lambda);
     std::cout << "U matrix of size " << X.d1 << ", " << k << std::endl;
     if (!getenv("PRIMALCR_NO_TEXT_DUMP")) write_text("U" + suffix + ".txt", U, X.d1, k);
     std::cout << "V matrix of size " << X.d2 << ", " << k << std::endl;
     if (!getenv("PRIMALCR_NO_TEXT_DUMP")) write_text("V" + suffix + ".txt", V, X.d2, k);
+    lap("cli: U.txt / V.txt text dumps");
     write_matrix(model_fp, U, X.d1, k);
     write_matrix(model_fp, V, X.d2, k);
     if (fclose(model_fp) != 0 || rename(model_tmp.c_str(), model.c_str()) != 0) {
         fprintf(stderr, "can't write model file %s\n", model.c_str());
         return 1;
     }
+    lap("cli: model file");
     return 0;
 }

@@ -30,6 +30,8 @@ struct NcclApi {
     int (*GetUniqueId)(pcr_ncclUniqueId *) = nullptr;
     int (*CommInitRank)(pcr_ncclComm_t *, int, pcr_ncclUniqueId, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, pcr_ncclComm_t, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(const void *, void *, size_t, int, int, pcr_ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, pcr_ncclComm_t, cudaStream_t) = nullptr;
     int (*CommDestroy)(pcr_ncclComm_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool load() {
@@ -40,9 +42,11 @@ struct NcclApi {
         GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+        ReduceScatter = (decltype(ReduceScatter))dlsym(h, "ncclReduceScatter");
+        AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
         CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+        return GetUniqueId && CommInitRank && AllReduce && ReduceScatter && AllGather && CommDestroy;
     }
 };
 static NcclApi g_nccl;
@@ -81,11 +85,9 @@ struct Engine {
     i64 *col_ptr = nullptr; int32_t *csc_user = nullptr, *csc2csr = nullptr;
     int32_t *cu_seg = nullptr; i64 *cu_start = nullptr, *cu_end = nullptr; i64 n_cunits = 0; i64 *col_unit_ptr = nullptr;
     int32_t *col_unit_idx = nullptr; int n_user_blocks = 1, n_item_blocks = 1;
-    // multi-GPU: the item-major pass runs one ITEM GROUP (balanced by ratings) at a time, so that the all-reduce of group g
-    // (comm stream) overlaps the row sums of group g+1 (compute stream)
-    static const int MAX_AR_GROUPS = 16;
-    int n_groups = 1; std::vector<i64> grp_unit0, grp_item0;
-    cudaStream_t comm_stream = nullptr; cudaEvent_t ev_grp[MAX_AR_GROUPS] = {nullptr}, ev_comm = nullptr;
+    // multi-GPU, large item sets: V-side vectors are reduce-scattered by item rows, the CG algebra runs on this rank's row
+    // slice and the search direction is all-gathered (see update_V); d2p = d2 rounded up to a multiple of the world size
+    bool sharded_cg = false; i64 d2p = 0, vs_row0 = 0, vs_rows = 0;
     // factors (padded leading dimension ld)
     double *U = nullptr, *V = nullptr;
     // per-rating work buffers
@@ -140,14 +142,6 @@ struct Engine {
             PCR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
             PCR_CUDA(cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, prio_hi));
         }
-        {
-            int prio_lo = 0, prio_hi = 0;
-            PCR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-            // the collective's few CTAs must get SM slots while a persistent row-sum grid of the next group is resident
-            PCR_CUDA(cudaStreamCreateWithPriority(&comm_stream, cudaStreamNonBlocking, prio_hi));
-            for (int q = 0; q < MAX_AR_GROUPS; ++q) PCR_CUDA(cudaEventCreateWithFlags(&ev_grp[q], cudaEventDisableTiming));
-            PCR_CUDA(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
-        }
         PCR_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         PCR_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         use_aux = getenv("PRIMALCR_NO_AUX_STREAM") == nullptr;
@@ -165,12 +159,8 @@ struct Engine {
     ~Engine() {
         cudaSetDevice(cfg.device);      // the communicator stays in the process-wide cache
         if (aux) cudaStreamSynchronize(aux);
-        if (comm_stream) cudaStreamSynchronize(comm_stream);
         if (stream) cudaStreamSynchronize(stream);
         prof.resolve();
-        for (int q = 0; q < MAX_AR_GROUPS; ++q) if (ev_grp[q]) cudaEventDestroy(ev_grp[q]);
-        if (ev_comm) cudaEventDestroy(ev_comm);
-        if (comm_stream) cudaStreamDestroy(comm_stream);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         if (aux) cudaStreamDestroy(aux);
@@ -475,50 +465,17 @@ struct Engine {
             sync();
             pool.raw_free(bpos_d);
             std::vector<int32_t> cseg, cidx; std::vector<i64> cstart, cend, csup((size_t)d2 + 1, 0);
-            // item groups for the pipelined all-reduce (one group when single-GPU): contiguous item ranges holding about
-            // the same number of ratings each
-            n_groups = 1;
-            if (world > 1) {
-                n_groups = getenv("PRIMALCR_AR_GROUPS") ? atoi(getenv("PRIMALCR_AR_GROUPS")) : 4;
-                n_groups = std::max(1, std::min<int>(std::min<i64>(n_groups, MAX_AR_GROUPS), d2));
-            }
-            grp_item0.assign((size_t)n_groups + 1, 0); grp_unit0.assign((size_t)n_groups + 1, 0);
-            if (n_groups > 1) {
-                // every rank must cut the items at the SAME places (the groups are all-reduced one by one): balance by the
-                // GLOBAL ratings per item = sum over ranks of this shard's column counts (exact in fp64)
-                std::vector<double> cnt((size_t)d2);
-                for (i64 pcol = 0; pcol < d2; ++pcol) cnt[pcol] = (double)(h_col[pcol + 1] - h_col[pcol]);
-                double *cnt_d = (double *)pool.raw_alloc(sizeof(double) * (size_t)d2);
-                PCR_CUDA(cudaMemcpyAsync(cnt_d, cnt.data(), sizeof(double) * (size_t)d2, cudaMemcpyHostToDevice, stream));
-                allreduce(cnt_d, (size_t)d2);
-                PCR_CUDA(cudaMemcpyAsync(cnt.data(), cnt_d, sizeof(double) * (size_t)d2, cudaMemcpyDeviceToHost, stream));
-                sync();
-                pool.raw_free(cnt_d);
-                double total = 0.0;
-                for (i64 pcol = 0; pcol < d2; ++pcol) total += cnt[pcol];
-                double run = 0.0; int gq = 1;
-                for (i64 pcol = 0; pcol < d2 && gq < n_groups; ++pcol) {
-                    run += cnt[pcol];
-                    while (gq < n_groups && run >= total * gq / n_groups) grp_item0[gq++] = pcol + 1;
-                }
-                for (; gq < n_groups; ++gq) grp_item0[gq] = d2;
-            }
-            grp_item0[n_groups] = d2;
-            for (int gq = 0; gq < n_groups; ++gq) {
-                grp_unit0[gq] = (i64)cseg.size();
-                for (int blk = 0; blk < nb; ++blk)
-                    for (i64 pcol = grp_item0[gq]; pcol < grp_item0[gq + 1]; ++pcol) {
-                        const i64 lo = bpos[(size_t)pcol * (nb + 1) + blk], hi = blk + 1 == nb ? h_col[pcol + 1] : bpos[(size_t)pcol * (nb + 1) + blk + 1];
-                        // popular items get longer units so that no item has more than ~48 + nb partial sums to add up
-                        const i64 collen = h_col[pcol + 1] - h_col[pcol];
-                        const i64 chunk = std::max<i64>(ROWSUM_CHUNK, (collen + 47) / 48);
-                        for (i64 bb = lo; bb < hi; bb += chunk) {
-                            cseg.push_back((int32_t)pcol); cstart.push_back(bb); cend.push_back(std::min(bb + chunk, hi));
-                            csup[pcol + 1] += 1;
-                        }
+            for (int blk = 0; blk < nb; ++blk)
+                for (i64 pcol = 0; pcol < d2; ++pcol) {
+                    const i64 lo = bpos[(size_t)pcol * (nb + 1) + blk], hi = blk + 1 == nb ? h_col[pcol + 1] : bpos[(size_t)pcol * (nb + 1) + blk + 1];
+                    // popular items get longer units so that no item has more than ~48 + nb partial sums to add up
+                    const i64 collen = h_col[pcol + 1] - h_col[pcol];
+                    const i64 chunk = std::max<i64>(ROWSUM_CHUNK, (collen + 47) / 48);
+                    for (i64 bb = lo; bb < hi; bb += chunk) {
+                        cseg.push_back((int32_t)pcol); cstart.push_back(bb); cend.push_back(std::min(bb + chunk, hi));
+                        csup[pcol + 1] += 1;
                     }
-            }
-            grp_unit0[n_groups] = (i64)cseg.size();
+                }
             n_cunits = (i64)cseg.size();
             for (i64 pcol = 0; pcol < d2; ++pcol) csup[pcol + 1] += csup[pcol];
             cidx.resize(cseg.size());
@@ -544,9 +501,18 @@ struct Engine {
             PCR_CUDA(cudaMemsetAsync(meta.ulev, 0, sizeof(uint16_t) * (size_t)d1 * 8, stream));
         }
         const size_t vn = (size_t)d2 * ld, un = (size_t)d1 * ld;
-        U = pool.alloc<double>(un); V = pool.alloc<double>(vn);
-        g = pool.alloc<double>(vn); delta = pool.alloc<double>(vn); rr = pool.alloc<double>(vn);
-        p = pool.alloc<double>(vn); Hp = pool.alloc<double>(vn); Vnew = pool.alloc<double>(vn);
+        U = pool.alloc<double>(un);
+        // V-side CG vectors: d2 rows padded to a multiple of the world size (equal row slices for reduce-scatter / all-gather;
+        // the padding rows stay zero).  Sharded CG algebra pays off once a vector is large: 64 MB by default
+        // (Netflix-shape 15.9 MB: one all-reduce is cheaper than reduce-scatter + 2 scalar all-reduces + all-gather).
+        d2p = world > 1 ? (d2 + world - 1) / world * world : d2;
+        vs_rows = d2p / std::max(world, 1); vs_row0 = (i64)rank * vs_rows;
+        sharded_cg = world > 1 && (double)vn * 8.0 >= 64e6;
+        if (const char *sc_env = getenv("PRIMALCR_SHARDED_CG")) sharded_cg = world > 1 && atoi(sc_env) != 0;
+        const size_t vnp = (size_t)d2p * ld;
+        g = pool.alloc<double>(vnp); delta = pool.alloc<double>(vnp); rr = pool.alloc<double>(vnp);
+        p = pool.alloc<double>(vnp); Hp = pool.alloc<double>(vnp); V = pool.alloc<double>(vnp); Vnew = pool.alloc<double>(vnp);
+        for (double *vec : {g, delta, rr, p, Hp, V, Vnew}) PCR_CUDA(cudaMemsetAsync(vec, 0, sizeof(double) * vnp, stream));
         partial = pool.alloc<double>((size_t)std::max(X.n_units, n_cunits) * ld);
         us.g = pool.alloc<double>(un); us.delta = pool.alloc<double>(un); us.rr = pool.alloc<double>(un);
         us.p = pool.alloc<double>(un); us.Hp = pool.alloc<double>(un); us.Unew = pool.alloc<double>(un);
@@ -653,12 +619,11 @@ struct Engine {
         return h_counters[which];
     }
     void zero_counters() { PCR_CUDA(cudaMemsetAsync(us.counters, 0, sizeof(int) * 4, stream)); }
-    void allreduce(double *buf, size_t n) { allreduce_on(stream, buf, n, "nccl_allreduce"); }
-    void allreduce_on(cudaStream_t st, double *buf, size_t n, const char *name) {
+    void allreduce(double *buf, size_t n) {
         if (world <= 1) return;
-        prof.begin(name, st, 0.0);
-        int r = g_nccl.AllReduce(buf, buf, n, PCR_NCCL_FLOAT64, PCR_NCCL_SUM, comm, st);
-        prof.end(st);
+        prof.begin("nccl_allreduce", stream, 0.0);
+        int r = g_nccl.AllReduce(buf, buf, n, PCR_NCCL_FLOAT64, PCR_NCCL_SUM, comm, stream);
+        prof.end(stream);
         if (r != 0) throw Error(PRIMALCR_ENCCL, std::string("ncclAllReduce failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
     }
     double pass_bytes(i64 n, i64 prows) const { return (double)n * (8.0 * k + 12.0) + 8.0 * k * (double)prows; }
@@ -740,28 +705,31 @@ struct Engine {
         if (world <= 1) {
             k_rowsum(ctx, cu_seg, cu_start, cu_end, n_cunits, col_unit_ptr, col_unit_idx, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
                      cfg.lambda, x, out, 0, bytes, k);
-            return;
+        } else {
+            k_rowsum(ctx, cu_seg, cu_start, cu_end, n_cunits, col_unit_ptr, col_unit_idx, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
+                     0.0, nullptr, out, 0, bytes, k);
+            allreduce(out, (size_t)d2 * ld);
+            k_axpby(ctx, out, 1.0, out, cfg.lambda, x, d2 * ld);
         }
-        // Multi-GPU: this rank's partial sums, one item group at a time; as soon as a group's rows are final its all-reduce
-        // starts on the (high-priority) comm stream and runs beside the row sums of the next group.  Only the last
-        // group's collective is exposed.  lambda*x is added after the reduction (every rank holds the same x).
-        for (int gq = 0; gq < n_groups; ++gq) {
-            const i64 u0 = grp_unit0[gq], nu = grp_unit0[gq + 1] - u0, s0 = grp_item0[gq], ns = grp_item0[gq + 1] - s0;
-            if (ns <= 0) continue;
-            k_rowsum(ctx, cu_seg + u0, cu_start + u0, cu_end + u0, nu, col_unit_ptr + s0, col_unit_idx, ns, csc_user, csc2csr, cbuf, U, ld,
-                     nullptr, partial, 0.0, nullptr, out + (size_t)s0 * ld, 0, bytes * (double)nu / (double)std::max<i64>(n_cunits, 1), k, u0);
-            if (n_groups == 1) { allreduce(out, (size_t)d2 * ld); break; }
-            PCR_CUDA(cudaEventRecord(ev_grp[gq], stream));
-            PCR_CUDA(cudaStreamWaitEvent(comm_stream, ev_grp[gq], 0));
-            allreduce_on(comm_stream, out + (size_t)s0 * ld, (size_t)ns * ld, "nccl_allreduce_overlapped");
-        }
-        if (n_groups > 1) {
-            PCR_CUDA(cudaEventRecord(ev_comm, comm_stream));
-            prof.begin("nccl_exposed_wait", stream, 0.0);      // what the compute stream actually waits for the collectives
-            PCR_CUDA(cudaStreamWaitEvent(stream, ev_comm, 0));
-            prof.end(stream);
-        }
-        k_axpby(ctx, out, 1.0, out, cfg.lambda, x, d2 * ld);
+    }
+    // Sharded form (multi-GPU, large d2): this rank's partial sums over ALL items, then a reduce-scatter by item rows -- only
+    // the rows [vs_row0, vs_row0 + vs_rows) of `out` hold the global sum (+ lambda x) afterwards
+    void rowsum_items_rs(const double *x, double *out) {
+        const double bytes = pass_bytes(X.nnz, d2);
+        k_rowsum(ctx, cu_seg, cu_start, cu_end, n_cunits, col_unit_ptr, col_unit_idx, d2, csc_user, csc2csr, cbuf, U, ld, nullptr, partial,
+                 0.0, nullptr, out, 0, bytes, k);
+        const size_t off = (size_t)vs_row0 * ld, n = (size_t)vs_rows * ld;
+        prof.begin("nccl_reduce_scatter", stream, 0.0);
+        int r = g_nccl.ReduceScatter(out, out + off, n, PCR_NCCL_FLOAT64, PCR_NCCL_SUM, comm, stream);     // in place
+        prof.end(stream);
+        if (r != 0) throw Error(PRIMALCR_ENCCL, "ncclReduceScatter failed");
+        k_axpby(ctx, out + off, 1.0, out + off, cfg.lambda, x + off, (i64)n);
+    }
+    void allgather_rows(double *vec) {      // every rank contributes its row slice of a d2p x ld vector
+        prof.begin("nccl_all_gather", stream, 0.0);
+        int r = g_nccl.AllGather(vec + (size_t)vs_row0 * ld, vec, (size_t)vs_rows * ld, PCR_NCCL_FLOAT64, comm, stream);   // in place
+        prof.end(stream);
+        if (r != 0) throw Error(PRIMALCR_ENCCL, "ncclAllGather failed");
     }
     // out[i] = lambda*x[i] + sum over user i of cbuf[e] * V[item(e)]   (U-side gradient / Hessian-vector product)
     void rowsum_users(const double *x, double *out, const uint8_t *active, int zero_if_empty) {
@@ -811,31 +779,65 @@ struct Engine {
             if (cfg.solver == 2) prepare(m, nullptr);
         }
         coeffs(0, nullptr);
-        rowsum_items(V, g);
+        if (sharded_cg) rowsum_items_rs(V, g); else rowsum_items(V, g);
         // prev_obj = objective(m, U, V): m and the sorted state do not change during CG, so evaluate it now
         if (!loss_matches_m) user_losses(m, nullptr);
         const double prev_obj = total_objective(U, V);
         // ---- solve_delta(_new): pcrpp.cpp:335-358
-        k_fill(ctx, delta, vn, 0.0);
-        k_axpby(ctx, rr, -1.0, g, 0.0, g, vn);
-        k_axpby(ctx, p, 1.0, g, 0.0, g, vn);
-        k_dot(ctx, rr, rr, vn, red_partials, slots + 0);
-        read_slots(1);
-        const double err = std::sqrt(h_slots[0]) * 0.01;
         int its = 0;
-        for (int it = 1; it <= 10; ++it) {
-            train_dots(U, p, b, nullptr);
-            coeffs(1, nullptr);
-            rowsum_items(p, Hp);
-            ++its;
-            // p.Hp, rr.p -> alpha (on the device) -> delta, rr updated -> rr.rr, rr.Hp: two fused passes, ONE host read
-            k_cg_dots2(ctx, p, Hp, rr, vn, red_partials, slots + 0);
-            k_cg_update(ctx, delta, rr, p, Hp, vn, slots + 0, red_partials, slots + 2);
-            read_slots(4);
-            const double prod_p_Hp = h_slots[0];
-            if (std::sqrt(h_slots[2]) < err) break;
-            const double beta = h_slots[3] / prod_p_Hp;
-            k_axpby(ctx, p, -1.0, rr, beta, p, vn);
+        if (!sharded_cg) {
+            k_fill(ctx, delta, vn, 0.0);
+            k_axpby(ctx, rr, -1.0, g, 0.0, g, vn);
+            k_axpby(ctx, p, 1.0, g, 0.0, g, vn);
+            k_dot(ctx, rr, rr, vn, red_partials, slots + 0);
+            read_slots(1);
+            const double err = std::sqrt(h_slots[0]) * 0.01;
+            for (int it = 1; it <= 10; ++it) {
+                train_dots(U, p, b, nullptr);
+                coeffs(1, nullptr);
+                rowsum_items(p, Hp);
+                ++its;
+                // p.Hp, rr.p -> alpha (on the device) -> delta, rr updated -> rr.rr, rr.Hp: two fused passes, ONE host read
+                k_cg_dots2(ctx, p, Hp, rr, vn, red_partials, slots + 0);
+                k_cg_update(ctx, delta, rr, p, Hp, vn, slots + 0, red_partials, slots + 2);
+                read_slots(4);
+                const double prod_p_Hp = h_slots[0];
+                if (std::sqrt(h_slots[2]) < err) break;
+                const double beta = h_slots[3] / prod_p_Hp;
+                k_axpby(ctx, p, -1.0, rr, beta, p, vn);
+            }
+        } else {
+            // Same recurrences on this rank's ROW SLICE of the V-side vectors (g was reduce-scattered above): the dot
+            // products are summed over ranks (2 x 2 scalars per iteration), the search direction p -- the only vector the
+            // next N*k pass needs in full -- is all-gathered, delta once at the end.  The replicated CG algebra (15 passes
+            // over d2 x k doubles per iteration, 1.4 ms at Yahoo-shape) shrinks by the world size.
+            const i64 sn = vs_rows * ld; const size_t so = (size_t)vs_row0 * ld;
+            double *g_s = g + so, *d_s = delta + so, *rr_s = rr + so, *p_s = p + so, *Hp_s = Hp + so;
+            k_fill(ctx, d_s, sn, 0.0);
+            k_axpby(ctx, rr_s, -1.0, g_s, 0.0, g_s, sn);
+            k_axpby(ctx, p_s, 1.0, g_s, 0.0, g_s, sn);
+            allgather_rows(p);
+            k_dot(ctx, rr_s, rr_s, sn, red_partials, slots + 0);
+            allreduce(slots, 1);
+            read_slots(1);
+            const double err = std::sqrt(h_slots[0]) * 0.01;
+            for (int it = 1; it <= 10; ++it) {
+                train_dots(U, p, b, nullptr);
+                coeffs(1, nullptr);
+                rowsum_items_rs(p, Hp);
+                ++its;
+                k_cg_dots2(ctx, p_s, Hp_s, rr_s, sn, red_partials, slots + 0);
+                allreduce(slots, 2);
+                k_cg_update(ctx, d_s, rr_s, p_s, Hp_s, sn, slots + 0, red_partials, slots + 2);
+                allreduce(slots + 2, 2);
+                read_slots(4);
+                const double prod_p_Hp = h_slots[0];
+                if (std::sqrt(h_slots[2]) < err) break;
+                const double beta = h_slots[3] / prod_p_Hp;
+                k_axpby(ctx, p_s, -1.0, rr_s, beta, p_s, sn);
+                allgather_rows(p);
+            }
+            allgather_rows(delta);
         }
         // ---- line search: pcrpp.cpp:427-441
         double stepsize = cfg.stepsize, now_obj = prev_obj;

@@ -204,8 +204,8 @@ bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 
 
 // ------------------------------------------------------------------ K4: segmented weighted row sums
 
-// L2 cache-policy loads (opt-in for the item-major pass, PRIMALCR_ROWSUM_L2HINT=1): the gathered U rows of the current user
-// block are asked to stay (evict_last), the ids / coefficients that stream through once are asked to leave first
+// L2 cache-policy loads of the item-major pass: the gathered U rows of the current user block are asked to stay
+// (evict_last), the ids / coefficients that stream through once are asked to leave first
 __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
     unsigned long long p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
 }
@@ -327,19 +327,19 @@ __global__ void __launch_bounds__(256) rowsum_finalize_kernel(const i64 *__restr
 void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_end, i64 n_units, const i64 *seg_unit_ptr,
               const int32_t *seg_unit_idx, i64 n_seg, const int32_t *ridx, const int32_t *widx, const double *w, const double *M, int ld,
               const uint8_t *active, double *partial, double lambda, const double *x, double *out,
-              int zero_if_empty, double bytes, int kk, i64 unit_base) {
+              int zero_if_empty, double bytes, int kk) {
     const int nch = (kk + 1) / 2;
-    double *partial_units = partial + (size_t)unit_base * ld;
     const int NCH = (nch + 31) / 32;
     PCR_REQUIRE(NCH <= 4, "rank too large for rowsum kernel (k <= 256)");
     const char *rs_name = widx ? "rowsum_items" : (active ? "rowsum_users_active" : "rowsum_users");
     if (n_units > 0) {
         PCR_CUDA(cudaMemsetAsync(c.ticket, 0, sizeof(unsigned long long), c.stream));
-        static const bool l2hint = getenv("PRIMALCR_ROWSUM_L2HINT") != nullptr && atoi(getenv("PRIMALCR_ROWSUM_L2HINT")) != 0;
+        // measured -2.3 % per item-major launch (profiles/experiments/README.md r02_rowsum_l2hint); PRIMALCR_ROWSUM_L2HINT=0 disables
+        static const bool l2hint = getenv("PRIMALCR_ROWSUM_L2HINT") == nullptr || atoi(getenv("PRIMALCR_ROWSUM_L2HINT")) != 0;
 #define RS(N) { if (l2hint && widx) { const unsigned grid = resident_grid(rowsum_kernel<N, true>, 256, 0, c.sms, (n_units + 7) / 8); \
-                  LAUNCH(c, rs_name, bytes, (rowsum_kernel<N, true>), grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial_units); } \
+                  LAUNCH(c, rs_name, bytes, (rowsum_kernel<N, true>), grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); } \
                 else { const unsigned grid = resident_grid(rowsum_kernel<N, false>, 256, 0, c.sms, (n_units + 7) / 8); \
-                  LAUNCH(c, rs_name, bytes, (rowsum_kernel<N, false>), grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial_units); } }
+                  LAUNCH(c, rs_name, bytes, (rowsum_kernel<N, false>), grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); } }
         switch (NCH) { case 1: RS(1) break; case 2: RS(2) break; case 3: RS(3) break; default: RS(4) break; }
 #undef RS
     }

@@ -39,9 +39,7 @@ bool k_dots_units(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 
 void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_end, i64 n_units, const i64 *seg_unit_ptr,
               const int32_t *seg_unit_idx, i64 n_seg, const int32_t *ridx, const int32_t *widx, const double *w, const double *M, int ld,
               const uint8_t *active, double *partial, double lambda, const double *x, double *out,
-              int zero_if_empty, double bytes, int kk, i64 unit_base = 0);
-// unit_base: the unit arrays passed in are a slice starting at global unit `unit_base` (seg_unit_idx holds GLOBAL unit ids and
-// `partial` is the global base): used to run the item-major pass one item group at a time (multi-GPU pipelining)
+              int zero_if_empty, double bytes, int kk);
 // per-user sort of scores (classes S and L, bitonic in shared memory); writes s / pos / lev
 void k_sort_users(Ctx &c, int cls, const int32_t *users, int n_users, const uint8_t *active, const i64 *row_ptr,
                   const double *m, const uint8_t *level, SortedMeta &meta);

@@ -97,12 +97,14 @@ def test_scale_parity_against_the_reference(case):
         assert abs(float((M * M).sum()) - float(g[nm + "_sq"])) <= max(1e-9, 10 * spread.max()) * float(g[nm + "_sq"]), nm
 
 
+@pytest.mark.parametrize("sharded_cg", [0, 1])
 @pytest.mark.parametrize("gpus", [2, 4, 8])
-def test_scale_parity_sharded_over_gpus(tmp_path, gpus):
+def test_scale_parity_sharded_over_gpus(tmp_path, gpus, sharded_cg):
     """The same Netflix-shape x 0.05 fixture through the C++ host driver with the users sharded over 2 / 4 / 8 GPUs (one
-    engine per GPU, item-group pipelined all-reduce of the V-side sums): printed objectives (6 digits) and the model file
-    against the reference's trajectory.  Each rank owns different items' ratings, so this is the test that sees a rank
-    reducing the wrong rows."""
+    engine per GPU): printed objectives (6 digits) and the model file against the reference's trajectory, for both forms
+    of the V-side exchange -- all-reduce + replicated CG algebra (default below 64 MB per vector) and reduce-scatter +
+    row-sliced CG algebra + all-gather (default above; 17,770 items do not divide by 4 or 8, so the padding rows are
+    exercised too).  Each rank holds different users' ratings of every item, so a rank that reduces the wrong rows shows."""
     import subprocess
     import torch
     from primalcr_b200.data import Dataset, Ratings, load_model, write_reference_dir
@@ -113,7 +115,7 @@ def test_scale_parity_sharded_over_gpus(tmp_path, gpus):
     exe = os.path.join(root, "primalcr_b200", "bin", "primalcr-train")
     write_reference_dir(str(tmp_path / "data"), Dataset(ds.train, Ratings.empty(ds.d1, ds.d2)))
     k, lam, iters = int(g["k"]), float(g["lam"]), int(g["iters"])
-    env = dict(os.environ, PRIMALCR_GPUS=str(gpus), PRIMALCR_NO_TEXT_DUMP="1")
+    env = dict(os.environ, PRIMALCR_GPUS=str(gpus), PRIMALCR_NO_TEXT_DUMP="1", PRIMALCR_SHARDED_CG=str(sharded_cg))
     out = subprocess.run([exe, "-s", "2", "-k", str(k), "-l", str(lam), "-t", str(iters), "-p", "0", "-n", "8",
                           str(tmp_path / "data"), str(tmp_path / "model")], cwd=tmp_path, capture_output=True, text=True,
                          env=env, timeout=600)

@@ -79,5 +79,51 @@ def stalls(path, regex, top=18, which=0):
         print("  %5.1f%% ex=%9s  %-58s %s" % (100 * int(r[i_s]) / tot, r[i_ex], r[i_src].strip()[:58], st))
 
 
+NAMES = {"rowsum_kernel": "rowsum_items", "dots_units_kernel": "dots", "tile_lm_sweep_kernel<1": "lm_sweep_hv",
+         "tile_prepare_kernel": "tile_prepare"}
+
+
+def traffic(full_rep, iter_csv, out_json):
+    """profiles/r02_traffic.json: per-launch DRAM bytes + L2 counters of the hot kernels (from ONE `ncu --set full` report) and
+    the DRAM bytes of a whole outer iteration (from a dram-bytes launch list of tools/profile_step.py)."""
+    import json
+    out = subprocess.run(["ncu", "-i", full_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    col = lambda r, name: float(r[hdr.index(name)].replace(",", ""))
+    scale = lambda name: {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[hdr.index(name)]]
+    kern = {}
+    for r in rows[2:]:
+        full = r[hdr.index("Kernel Name")]
+        # the item-major row sum is the rowsum_kernel launch that takes the L2-hint instantiation (or, without it, the first one)
+        key = next((v for k, v in NAMES.items() if k in full), None)
+        if key is None:
+            continue
+        if key == "rowsum_items" and "true" not in full and "rowsum_items" in kern:
+            continue
+        if key in kern and not (key == "rowsum_items" and "true" in full):
+            continue
+        rd = col(r, "dram__bytes_read.sum") * scale("dram__bytes_read.sum")
+        wr = col(r, "dram__bytes_write.sum") * scale("dram__bytes_write.sum")
+        kern[key] = {"kernel": full.split("(")[0], "dram_bytes_per_launch": rd + wr, "dram_read_bytes_per_launch": rd,
+                     "lts_throughput_pct": col(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+                     "l2_hit_pct": col(r, "lts__t_sector_hit_rate.pct"), "l1tex_hit_pct": col(r, "l1tex__t_sector_hit_rate.pct"),
+                     "duration_ms_under_ncu": col(r, "gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}[units[hdr.index("gpu__time_duration.sum")]]}
+    it = {"dram_bytes": 0.0, "launches": 0, "time_ms_under_ncu": 0.0}
+    lines = [l for l in open(iter_csv).read().splitlines() if l.startswith('"')]
+    for row in csv.DictReader(io.StringIO("\n".join(lines))):
+        v = float(row["Metric Value"].replace(",", ""))
+        if row["Metric Name"].startswith("dram__bytes"):
+            it["dram_bytes"] += v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[row["Metric Unit"]]
+        elif row["Metric Name"] == "gpu__time_duration.sum":
+            it["launches"] += 1; it["time_ms_under_ncu"] += v * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[row["Metric Unit"]]
+    json.dump({"_note": "ncu of the round-2 tree, Netflix-shape k=100 at full size on one B200: kernels = one `ncu --set full "
+                        "--clock-control none` launch each (tools/gpu/r02_capture.sh -> %s); iteration = dram__bytes_read+write "
+                        "summed over every launch of ONE outer iteration (%s)" % (full_rep.split("/")[-1], iter_csv.split("/")[-1]),
+               "workload": {"shape": "netflix", "scale": 1.0, "k": 100, "n_gpus": 1}, "kernels": kern, "iteration": it},
+              open(out_json, "w"), indent=1)
+    print(json.dumps({"kernels": kern, "iteration": it}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw, "stalls": stalls}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "raw": raw, "stalls": stalls, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
