@@ -218,10 +218,9 @@ __device__ __forceinline__ double2 ldg_hint_d2(const double2 *p, unsigned long l
 __device__ __forceinline__ int ldg_hint_i32(const int32_t *p, unsigned long long pol) {
     int v; asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v;
 }
-__device__ __forceinline__ double ldg_hint_f64(const double *p, unsigned long long pol) {
-    double v; asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol)); return v;
-}
 
+// HINT: gathered rows evict_last, the two id streams evict_first; the coefficient gather keeps the default policy (its
+// 32-byte sectors hold 4 coefficients that other items' units read soon: evict_first there cost +3 GB of DRAM reads per launch)
 template <int NCH, bool HINT = false>
 __global__ void __launch_bounds__(256, PCR_ROWSUM_MINB) rowsum_kernel(const int32_t *__restrict__ un_seg, const i64 *__restrict__ un_start,
                                                      const i64 *__restrict__ un_end,
@@ -248,7 +247,7 @@ __global__ void __launch_bounds__(256, PCR_ROWSUM_MINB) rowsum_kernel(const int3
             const i64 me = base + lane;
             int ri = 0; double wi = 0.0;
             if (me < e) {
-                if (HINT) { ri = ldg_hint_i32(ridx + me, pol_stream); wi = ldg_hint_f64(w + ldg_hint_i32(widx + me, pol_stream), pol_stream); }
+                if (HINT) { ri = ldg_hint_i32(ridx + me, pol_stream); wi = w[ldg_hint_i32(widx + me, pol_stream)]; }
                 else { ri = ridx[me]; wi = widx ? w[widx[me]] : w[me]; }
             }
             const int cnt = (e - base) < 32 ? (int)(e - base) : 32;
@@ -336,12 +335,12 @@ void k_rowsum(Ctx &c, const int32_t *un_seg, const i64 *un_start, const i64 *un_
         PCR_CUDA(cudaMemsetAsync(c.ticket, 0, sizeof(unsigned long long), c.stream));
         // measured -2.3 % per item-major launch (profiles/experiments/README.md r02_rowsum_l2hint); PRIMALCR_ROWSUM_L2HINT=0 disables
         static const bool l2hint = getenv("PRIMALCR_ROWSUM_L2HINT") == nullptr || atoi(getenv("PRIMALCR_ROWSUM_L2HINT")) != 0;
-#define RS(N) { if (l2hint && widx) { const unsigned grid = resident_grid(rowsum_kernel<N, true>, 256, 0, c.sms, (n_units + 7) / 8); \
-                  LAUNCH(c, rs_name, bytes, (rowsum_kernel<N, true>), grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); } \
-                else { const unsigned grid = resident_grid(rowsum_kernel<N, false>, 256, 0, c.sms, (n_units + 7) / 8); \
-                  LAUNCH(c, rs_name, bytes, (rowsum_kernel<N, false>), grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); } }
+#define RSL(N, H) { const unsigned grid = resident_grid(rowsum_kernel<N, H>, 256, 0, c.sms, (n_units + 7) / 8); \
+                  LAUNCH(c, rs_name, bytes, (rowsum_kernel<N, H>), grid, 256, 0, un_seg, un_start, un_end, n_units, c.ticket, ridx, widx, w, M, ld, nch, active, partial); }
+#define RS(N) { if (l2hint && widx) RSL(N, true) else RSL(N, false) }
         switch (NCH) { case 1: RS(1) break; case 2: RS(2) break; case 3: RS(3) break; default: RS(4) break; }
 #undef RS
+#undef RSL
     }
     if (n_seg > 0)
         LAUNCH(c, "rowsum_finalize", 0.0, rowsum_finalize_kernel, grid_for(n_seg, 8, c.sms * 8), 256, 0, seg_unit_ptr, seg_unit_idx, n_seg,

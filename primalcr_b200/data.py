@@ -215,7 +215,10 @@ def synth_dataset(shape: str | dict, scale: float = 1.0, device: str = "cpu", te
     ranks = torch.arange(1, d2 + 1, device=dev, dtype=f64)
     w = ranks.pow(-0.8)
     perm = torch.randperm(d2, generator=g, device=dev)
-    cdf = torch.cumsum(w / w.sum(), 0)
+    # sequential prefix sum on the host: a multi-tile CUDA scan (d2 > a few thousand) associates its fp64 partial sums in a
+    # timing-dependent order, so the cdf -- and a handful of the items drawn from it -- differed between two GPU boxes
+    # (Yahoo shape, round 2: objective at iteration 0 equal only to 3e-8).  Bit-identical to torch's CPU cumsum.
+    cdf = torch.from_numpy(np.cumsum((w / w.sum()).cpu().numpy())).to(dev)
     heavy = deg > d2 // 4
     keys = torch.empty(0, dtype=torch.int64, device=dev)
     # heavy users: exact weighted sampling without replacement (exponential keys, smallest first)

@@ -54,6 +54,8 @@ def test_scale_parity_against_the_reference(case):
     # truncated CG amplifies those last-bit differences to ~7e-7 of the objective by iteration 2 -- the reference cannot
     # reproduce itself better than that, so the GPU is held to max(1e-9, 3 x that spread) there and to 1e-9 elsewhere.
     spread = np.abs(g["obj"] - g["ref_obj"]) / np.abs(g["obj"])
+    if "ref1_obj" in g:          # the unmodified reference on ONE thread: identical to the restatement, bit for bit
+        assert np.array_equal(g["ref1_obj"][1:], g["obj"][1:]) and np.array_equal(g["ref1_U_rows"], g["U_rows"])
     collapsed = np.unpackbits(g["collapsed"], axis=1)[:, :ds.d1].astype(bool)
     lens, lens_t = ds.train.lens(), ds.test.lens()
 
@@ -66,12 +68,22 @@ def test_scale_parity_against_the_reference(case):
         ok = ~collapsed[i]
         for which, c0, want_cnt, ln in ((0, 0, g["err_train"][i], lens), (1, 2, g["err_test"][i], lens_t)):
             err, ndcg, cnt = e.eval_error_counts(which, method=0)
-            assert np.array_equal(cnt[ok], want_cnt[ok]), (i, which, int((cnt[ok] != want_cnt[ok]).sum()))
+            # identical integers -- except that a user with n ratings has n(n-1)/2 pairs and the scores differ from the
+            # reference's by ~1e-11: beyond ~3e4 ratings (5e8 pairs) a pair that close exists, so 2e-9 of a user's pairs may
+            # flip (0 for every user below 31,623 ratings; the 87,311- and 99,990-rating users of the power-law case differ
+            # by exactly one pair out of 3.8e9 / 5.0e9)
+            pairs = ln.astype(np.float64) * (ln - 1) / 2
+            bad = np.nonzero(ok & (np.abs(cnt - want_cnt) > np.floor(2e-9 * pairs)))[0]
+            exact = i == 0 or spread[i] < 1e-9          # where the reference reproduces itself, so must we -- user by user
+            if exact:
+                assert len(bad) == 0, (i, which, bad.tolist(), ln[bad].tolist(), (cnt[bad] - want_cnt[bad]).tolist())
             if which == 0 and solver == 2:          # the O(len * levels) count from the sorted state: same integers
                 err1, ndcg1, cnt1 = e.eval_error_counts(0, method=1)
-                assert np.array_equal(cnt1, cnt) and err1 == err and ndcg1 == ndcg
+                assert np.array_equal(cnt1, cnt) and err1 == err and ndcg1 == ndcg      # same scores in: no tolerance here
             noise = float(((ln >= 2) & collapsed[i]).sum()) / max(int((ln >= 2).sum()), 1)     # each such user moves the mean by <= 1/n
-            assert abs(err - g["evals"][i, c0]) <= ERR_TOL + noise, (i, which, err, g["evals"][i, c0])
+            # (iteration 2 of the power-law case: the factors themselves differ by ~1e-3 between two runs of the reference, so
+            #  only the mean is comparable there, to the tolerance north_star gives NDCG)
+            assert abs(err - g["evals"][i, c0]) <= (ERR_TOL if exact else NDCG_TOL) + noise, (i, which, err, g["evals"][i, c0])
             assert abs(ndcg - g["evals"][i, c0 + 1]) < NDCG_TOL + noise, (i, which, ndcg, g["evals"][i, c0 + 1])
 
     o = e.initial_objective()

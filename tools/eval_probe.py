@@ -18,10 +18,14 @@ def main():
     e = api.Engine(api.Parameter(solver_type=2, k=a.k, lambda_=5000.0, maxiter=1, do_predict=1))
     e.set_levels(np.arange(1, 6)); e.set_train(ds.train); e.set_test(ds.test); e.set_factors(U, V)
     e.initial_objective(); e.outer_iteration()
-    out = {}
-    for which, name in ((0, "train"), (1, "test")):
+    torch.cuda.synchronize(); t = time.time(); e.outer_iteration(); torch.cuda.synchronize()
+    out = {"outer_iteration_sec": time.time() - t}
+    # method -1: what primalcr_eval picks (sorted-state count for the Primal-CR++ training set), 0: all pairs, 1: sorted state
+    for which, name, method in ((0, "train_auto", -1), (0, "train_all_pairs", 0), (0, "train_sorted", 1), (1, "test", -1)):
         e.profile_enable(True); e.profile_reset()
-        torch.cuda.synchronize(); t = time.time(); r = e.eval(which); torch.cuda.synchronize(); dt = time.time() - t
+        torch.cuda.synchronize(); t = time.time()
+        r = e.eval(which) if method < 0 else e.eval_error_counts(which, method)[:2]
+        torch.cuda.synchronize(); dt = time.time() - t
         prof = e.profile(); e.profile_enable(False)
         out[name] = dict(sec=dt, result=r, kernels={n: round(v["ms"], 3) for n, v in prof.items() if v["ms"] > 0.01})
     print(json.dumps(dict(workload=a.workload, scale=a.scale, nnz=ds.train.nnz, max_len=int(ds.train.lens().max()), **out)))

@@ -13,3 +13,10 @@ python tools/dump_csr.py --workload netflix --dir /dev/shm/nf > gpurun_out/r02ca
 ls -la /dev/shm/nf /dev/shm/nf.model >> gpurun_out/r02_cli_full_size.log 2>&1
 rm -rf /dev/shm/nf /dev/shm/nf.model /dev/shm/U.txt /dev/shm/V.txt
 tail -20 gpurun_out/r02_cli_full_size.log
+# (5) cp.async row-sum variant A/B (stage level) and the power-law scale fixture
+for cfg in "base:" "cpasync:PRIMALCR_ROWSUM_CPASYNC=1"; do
+  tag=${cfg%%:*}; envs=${cfg#*:}
+  env $envs timeout 300 python tools/stage_bench.py --side VU --tag $tag >> gpurun_out/r02cap_stage.jsonl 2>> gpurun_out/r02cap_stage.err; echo "stage $tag rc=$?"
+done
+cat gpurun_out/r02cap_stage.jsonl
+timeout 900 python -m pytest tests/test_gpu_scale.py -m gpu -q -k "powerlaw001" > gpurun_out/r02cap_pytest_powerlaw.log 2>&1; echo "pytest powerlaw rc=$?"; tail -5 gpurun_out/r02cap_pytest_powerlaw.log
