@@ -890,9 +890,14 @@ struct Engine {
         for (int it = 1; it <= 10 && n_active > 0; ++it) {
             train_dots(us.p, V, b, us.cg_active);
             coeffs(1, us.cg_active);
-            rowsum_users(us.p, us.Hp, us.cg_active, 0);
             zero_counters();
-            k_u_cg_step(ctx, us, d1, ld);
+            // unit partials of V_i^T c, then finalize (Hs = lambda s + sum) fused with the user's CG recurrences
+            k_rowsum(ctx, X.un_seg, X.un_start, X.un_end, X.n_units, X.seg_unit_ptr, X.seg_unit_idx, /*n_seg=*/0, X.item, nullptr, cbuf, V, ld,
+                     us.cg_active, partial, cfg.lambda, us.p, us.Hp, 0, 0.0, k);
+            if (!k_u_finalize_cg(ctx, X.seg_unit_ptr, X.seg_unit_idx, partial, us, d1, ld, k, cfg.lambda)) {
+                rowsum_users(us.p, us.Hp, us.cg_active, 0);
+                k_u_cg_step(ctx, us, d1, ld);
+            }
             n_active = read_counter(0);
         }
         // ---- line search: <= 20 halvings per user; the last trial is kept even if it never decreased (:814)

@@ -1009,6 +1009,84 @@ __global__ void __launch_bounds__(256) u_cg_step_vec_kernel(UState s, i64 d1, in
     }
 }
 
+// rowsum_finalize (user side) + u_cg_step in one pass: the warp that adds up a user's partial rows into Hp = lambda p + V_i^T c
+// keeps the row in registers and runs the user's CG recurrences on it right away -- Hp is never written or re-read and one
+// launch per CG round goes away.  Same additions in the same order as the two separate kernels (bit-identical state).
+template <int NV>
+__global__ void __launch_bounds__(256) u_finalize_cg_kernel(const i64 *__restrict__ seg_unit_ptr, const int32_t *__restrict__ seg_unit_idx,
+                                                            const double *__restrict__ partial, UState s, i64 d1, int ld, int kp,
+                                                            double lambda) {
+    const int lane = threadIdx.x & 31;
+    const i64 i = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (i >= d1) return;
+    if (!s.cg_active[i]) return;
+    const size_t o = (size_t)i * ld;
+    const int n2 = ld >> 1, nch = kp >> 1;
+    double2 *p2 = reinterpret_cast<double2 *>(s.p + o), *r2 = reinterpret_cast<double2 *>(s.rr + o);
+    double2 *d2p = reinterpret_cast<double2 *>(s.delta + o);
+    double2 p[NV], hp[NV], rr[NV], dl[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const int c = lane + 32 * q;
+        const double2 z = make_double2(0.0, 0.0);
+        p[q] = c < n2 ? p2[c] : z; rr[q] = c < n2 ? r2[c] : z; dl[q] = c < n2 ? d2p[c] : z;
+        hp[q] = c < nch ? make_double2(lambda * p[q].x, lambda * p[q].y) : z;        // rowsum_finalize: v = lambda * x ...
+    }
+    for (i64 u = seg_unit_ptr[i]; u < seg_unit_ptr[i + 1]; ++u) {                    // ... + the unit partials, in list order
+        const double2 *prow = reinterpret_cast<const double2 *>(partial + (size_t)(seg_unit_idx ? seg_unit_idx[u] : u) * ld);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const int c = lane + 32 * q;
+            if (c < nch) { const double2 t = prow[c]; hp[q].x += t.x; hp[q].y += t.y; }
+        }
+    }
+    double pHp = 0.0, rp = 0.0;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        pHp = fma(p[q].x, hp[q].x, pHp); pHp = fma(p[q].y, hp[q].y, pHp);
+        rp = fma(rr[q].x, p[q].x, rp); rp = fma(rr[q].y, p[q].y, rp);
+    }
+    pHp = warp_sum(pHp); rp = warp_sum(rp);
+    const double alpha = -1.0 * rp / pHp;
+    double nr = 0.0, rHp = 0.0;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        dl[q].x = dl[q].x + p[q].x * alpha; dl[q].y = dl[q].y + p[q].y * alpha;
+        rr[q].x = rr[q].x + hp[q].x * alpha; rr[q].y = rr[q].y + hp[q].y * alpha;
+        nr = fma(rr[q].x, rr[q].x, nr); nr = fma(rr[q].y, rr[q].y, nr);
+        rHp = fma(rr[q].x, hp[q].x, rHp); rHp = fma(rr[q].y, hp[q].y, rHp);
+    }
+    nr = warp_sum(nr); rHp = warp_sum(rHp);
+    const int its = s.cg_its[i] + 1;
+    const bool done = (sqrt(nr) < s.err[i]) || (its >= 10);
+    const double beta = rHp / pHp;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const int c = lane + 32 * q;
+        if (c < n2) {
+            d2p[c] = dl[q]; r2[c] = rr[q];
+            if (!done) p2[c] = make_double2(-rr[q].x + p[q].x * beta, -rr[q].y + p[q].y * beta);
+        }
+    }
+    if (lane == 0) {
+        s.cg_its[i] = its;
+        if (done) s.cg_active[i] = 0; else atomicAdd(&s.counters[0], 1);
+    }
+}
+
+// returns false when ld is too large for the register-resident form (caller runs finalize + k_u_cg_step instead)
+bool k_u_finalize_cg(Ctx &c, const i64 *seg_unit_ptr, const int32_t *seg_unit_idx, const double *partial, UState &s, i64 d1, int ld,
+                     int kk, double lambda) {
+    if (d1 <= 0) return true;
+    if (ld > 256) return false;
+    const unsigned grid = (unsigned)((d1 + 7) / 8);
+    const int kp = 2 * ((kk + 1) / 2);
+    if (ld <= 64) LAUNCH(c, "u_finalize_cg", 0.0, u_finalize_cg_kernel<1>, grid, 256, 0, seg_unit_ptr, seg_unit_idx, partial, s, d1, ld, kp, lambda);
+    else if (ld <= 128) LAUNCH(c, "u_finalize_cg", 0.0, u_finalize_cg_kernel<2>, grid, 256, 0, seg_unit_ptr, seg_unit_idx, partial, s, d1, ld, kp, lambda);
+    else LAUNCH(c, "u_finalize_cg", 0.0, u_finalize_cg_kernel<4>, grid, 256, 0, seg_unit_ptr, seg_unit_idx, partial, s, d1, ld, kp, lambda);
+    return true;
+}
+
 __global__ void __launch_bounds__(256) u_ls_begin_kernel(UState s, i64 d1, double stepsize0) {
     const i64 i = (i64)blockIdx.x * 256 + threadIdx.x;
     if (i >= d1) return;

@@ -84,6 +84,9 @@ struct UState {
 void k_u_init(Ctx &c, UState &s, const double *U, const i64 *row_ptr, const uint8_t *has_pairs, i64 d1, int ld,
               double lambda);
 void k_u_cg_step(Ctx &c, UState &s, i64 d1, int ld);
+// the user-side rowsum_finalize (Hp = lambda p + unit partials) and k_u_cg_step in one pass; false: ld too large, not launched
+bool k_u_finalize_cg(Ctx &c, const i64 *seg_unit_ptr, const int32_t *seg_unit_idx, const double *partial, UState &s, i64 d1, int ld,
+                     int kk, double lambda);
 void k_u_ls_trial(Ctx &c, UState &s, const double *U, i64 d1, int ld, double stepsize0, int first);
 void k_u_ls_check(Ctx &c, UState &s, i64 d1, int ld, double lambda, int last);
 void k_u_commit(Ctx &c, UState &s, double *U, i64 d1, int ld);
