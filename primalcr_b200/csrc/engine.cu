@@ -80,6 +80,7 @@ struct Engine {
     DevCsr X, XT;
     bool has_train = false, has_test = false, has_factors = false, use_tiles = true;
     bool ratings_integer = false;     // every training rating equals its lround: levels order ratings like the exact doubles
+    double *level_vals = nullptr;     // [8] the level table as doubles (NDCG gains from the sorted state)
     i64 *ev_err_user = nullptr;
     // CSC of the training set (by item)
     i64 *col_ptr = nullptr; int32_t *csc_user = nullptr, *csc2csr = nullptr;
@@ -295,6 +296,11 @@ struct Engine {
                 levels = distinct;
             }
             T = (int)levels.size();
+            {
+                std::vector<double> lv(std::max<size_t>(levels.size(), 8), 0.0);
+                for (size_t q = 0; q < levels.size(); ++q) lv[q] = (double)levels[q];
+                level_vals = upload_vec(lv);
+            }
             i64 *tab = upload_vec(levels);
             int *bad = pool.alloc<int>(1);
             PCR_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), stream));
@@ -968,9 +974,12 @@ struct Engine {
         if (which == 0 && scores_valid) sc = m;                      // m already holds U_i . V_j of the current factors
         else if (which == 0) train_dots(U, V, sc, nullptr);           // user-major units kernel (2x the generic one)
         else k_dots(ctx, U, C.user, V, C.item, C.nnz, ld, k, nullptr, sc, 0.0);
-        if (sorted) k_eval_sorted(ctx, C, meta, T, ev_err_user);
-        else k_eval_pairs(ctx, C, sc, ev_err_item);
-        k_eval_users(ctx, C, sc, sorted ? ev_err_user : ev_err_item, sorted ? 1 : 0, cfg.ndcg_k, ev_a, ev_b, ev_c, ev_d);
+        if (sorted) {       // pair errors AND NDCG@k of every user from the sorted state, one kernel
+            k_eval_sorted(ctx, C, meta, T, ev_err_user, level_vals, cfg.ndcg_k, ev_a, ev_b, ev_c, ev_d);
+        } else {
+            k_eval_pairs(ctx, C, sc, ev_err_item);
+            k_eval_users(ctx, C, sc, ev_err_item, 0, cfg.ndcg_k, ev_a, ev_b, ev_c, ev_d);
+        }
         if (err_user_host) {
             if (!sorted) k_eval_item_to_user(ctx, C, ev_err_item, ev_err_user);
             if (C.d1) PCR_CUDA(cudaMemcpyAsync(err_user_host, ev_err_user, sizeof(i64) * (size_t)C.d1, cudaMemcpyDeviceToHost, stream));

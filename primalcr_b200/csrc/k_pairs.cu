@@ -180,9 +180,16 @@ void k_eval_pairs(Ctx &c, const DevCsr &X, const double *score, i64 *err_item) {
 // reference compares, util.cpp:468-474) -- the engine checks that and otherwise keeps the all-pairs kernel above.
 // One warp per user walks the sorted positions 32 at a time: per-level ballots give the in-chunk prefix counts, two
 // small carried tables hold the counts before the chunk and at the start of a run of ties that began in an earlier chunk.
+// The same warp also produces the user's NDCG@k from the sorted state (util.cpp:494-531): the k best-scored ratings are the
+// tail of the ascending order (runs of equal scores taken smallest position first, as the arg-max kernel below does), the
+// ideal ordering follows from the per-level totals (integer ratings: rating == level value).
 template <int T>
 __global__ void __launch_bounds__(256) eval_sorted_kernel(const i64 *__restrict__ row_ptr, i64 d1, const double *__restrict__ s_sorted,
-                                                          const uint8_t *__restrict__ lev_sorted, i64 *__restrict__ err_user) {
+                                                          const uint8_t *__restrict__ lev_sorted, i64 *__restrict__ err_user,
+                                                          const int32_t *__restrict__ pos_sorted, const double *__restrict__ rating,
+                                                          const double *__restrict__ level_vals, int ndcg_k,
+                                                          double *__restrict__ err_ratio, double *__restrict__ ndcg,
+                                                          double *__restrict__ has_pair, double *__restrict__ has_any) {
     const int lane = threadIdx.x & 31;
     const i64 u = ((i64)blockIdx.x * 256 + threadIdx.x) >> 5;
     if (u >= d1) return;
@@ -231,14 +238,42 @@ __global__ void __launch_bounds__(256) eval_sorted_kernel(const i64 *__restrict_
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(FULL, err, o);
-    if (lane == 0) err_user[u] = err;
+    if (lane != 0) return;
+    err_user[u] = err;
+    if (ndcg == nullptr) return;
+    if (n == 0) { err_ratio[u] = 0.0; ndcg[u] = 0.0; has_pair[u] = 0.0; has_any[u] = 0.0; return; }
+    const i64 num = (i64)n * (n - 1) / 2;
+    has_any[u] = 1.0;
+    if (num != 0) { err_ratio[u] = (double)err / (double)num; has_pair[u] = 1.0; }
+    else { err_ratio[u] = 0.0; has_pair[u] = 0.0; }
+    const int nowk = ndcg_k < n ? ndcg_k : n;
+    double dcg = 0.0, idcg = 0.0;
+    int r = 0, j = n - 1;
+    while (r < nowk) {                                   // runs of equal scores from the top, each in ascending position order
+        int a = j;
+        const double sj = s_sorted[start + j];
+        while (a > 0 && s_sorted[start + a - 1] == sj) --a;
+        for (int q = a; q <= j && r < nowk; ++q, ++r)
+            dcg += (exp2(rating[pos_sorted[start + q]]) - 1.0) / log2((double)(r + 1) + 1.0);
+        j = a - 1;
+    }
+    r = 0;
+#pragma unroll
+    for (int t = T - 1; t >= 0; --t) {
+        const double gain = exp2(level_vals[t]) - 1.0;
+        for (int q = 0; q < total[t] && r < nowk; ++q, ++r) idcg += gain / log2((double)(r + 1) + 1.0);
+    }
+    ndcg[u] = dcg / idcg;
 }
 
-void k_eval_sorted(Ctx &c, const DevCsr &X, const SortedMeta &meta, int T, i64 *err_user) {
+void k_eval_sorted(Ctx &c, const DevCsr &X, const SortedMeta &meta, int T, i64 *err_user, const double *level_vals, int ndcg_k,
+                   double *err_ratio_user, double *ndcg_user, double *has_pair_user, double *has_any_user) {
     if (X.d1 <= 0) return;
     const unsigned grid = (unsigned)((X.d1 + 7) / 8);
-    if (T <= 5) LAUNCH(c, "eval_sorted", 0.0, eval_sorted_kernel<5>, grid, 256, 0, X.row_ptr, X.d1, meta.s, meta.lev, err_user);
-    else        LAUNCH(c, "eval_sorted", 0.0, eval_sorted_kernel<8>, grid, 256, 0, X.row_ptr, X.d1, meta.s, meta.lev, err_user);
+#define ES(TT) LAUNCH(c, "eval_sorted", 0.0, eval_sorted_kernel<TT>, grid, 256, 0, X.row_ptr, X.d1, meta.s, meta.lev, err_user, meta.pos, X.rating, \
+                      level_vals, ndcg_k, err_ratio_user, ndcg_user, has_pair_user, has_any_user)
+    if (T <= 5) ES(5); else ES(8);
+#undef ES
 }
 
 // per user: error ratio, NDCG@k (top-k by repeated arg-max; ties -> smaller index).  One WARP per user: the arg-max is a

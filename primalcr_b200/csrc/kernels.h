@@ -115,7 +115,9 @@ void k_has_pairs(Ctx &c, const DevCsr &X, uint8_t *has_pairs);
 // evaluation: pair errors per work item -> per user ratio; ndcg per user
 void k_eval_pairs(Ctx &c, const DevCsr &X, const double *score, i64 *err_item);
 // the same integer per USER from the sorted state (O(len * T), integer ratings only; T <= 8)
-void k_eval_sorted(Ctx &c, const DevCsr &X, const SortedMeta &meta, int T, i64 *err_user);
+// ndcg_user != nullptr: also the per-user error ratio / NDCG@k / has-pair / has-any outputs of k_eval_users, from the same state
+void k_eval_sorted(Ctx &c, const DevCsr &X, const SortedMeta &meta, int T, i64 *err_user, const double *level_vals, int ndcg_k,
+                   double *err_ratio_user, double *ndcg_user, double *has_pair_user, double *has_any_user);
 void k_eval_item_to_user(Ctx &c, const DevCsr &X, const i64 *err_item, i64 *err_user);
 // err_per_user != 0: err_item holds one count per user (k_eval_sorted) instead of one per pair work item
 void k_eval_users(Ctx &c, const DevCsr &X, const double *score, const i64 *err_item, int err_per_user, int ndcg_k,

@@ -79,8 +79,8 @@ def stalls(path, regex, top=18, which=0):
         print("  %5.1f%% ex=%9s  %-58s %s" % (100 * int(r[i_s]) / tot, r[i_ex], r[i_src].strip()[:58], st))
 
 
-NAMES = {"rowsum_kernel": "rowsum_items", "dots_units_kernel": "dots", "tile_lm_sweep_kernel<1": "lm_sweep_hv",
-         "tile_prepare_kernel": "tile_prepare"}
+NAMES = {"rowsum_kernel": "rowsum_items", "dots_units_kernel": "dots", "tile_lm_sweep_kernel<1, 5, 256>": "lm_sweep_hv",
+         "tile_prepare_kernel<5, 256>": "tile_prepare"}
 
 
 def traffic(full_rep, iter_csv, out_json):
