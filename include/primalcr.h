@@ -165,6 +165,9 @@ void primalcr_dataset_free(primalcr_dataset *ds);
 /* initial() util.cpp:80-93: default-seeded std::default_random_engine + normal_distribution<double>(0,1),
    row-major fill.  A fresh engine per call, so V equals the first d2 rows of U, as in the reference. */
 void primalcr_reference_init(double *out, int64_t n, int64_t k);
+/* The U.txt / V.txt side files of run_pcr / run_pcrpp (pmf-train.cpp:209-227, 276-295: `myfile << U[i][j]`, 6 significant
+   digits, space separated, one row per line), formatted on all host threads; byte-identical to the reference's stream. */
+int primalcr_write_text_matrix(const char *path, const double *M, int64_t rows, int k);
 
 #ifdef __cplusplus
 }

@@ -52,7 +52,7 @@ SYMBOLS = [
     "primalcr_level_counts", "primalcr_num_levels", "primalcr_objective", "primalcr_grad_V", "primalcr_hv_V",
     "primalcr_grad_U", "primalcr_hv_U", "primalcr_stream", "primalcr_launch_count", "primalcr_profile_enable",
     "primalcr_profile_reset", "primalcr_profile_count", "primalcr_profile_get", "primalcr_device_bytes",
-    "primalcr_reference_init", "primalcr_predict", "primalcr_load_dir", "primalcr_dataset_info",
+    "primalcr_reference_init", "primalcr_write_text_matrix", "primalcr_predict", "primalcr_load_dir", "primalcr_dataset_info",
     "primalcr_dataset_csr", "primalcr_dataset_free",
 ]
 
@@ -115,6 +115,7 @@ def lib():
                                        C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.primalcr_device_bytes.argtypes = [vp]; L.primalcr_device_bytes.restype = C.c_int64
     L.primalcr_reference_init.argtypes = [f64p, C.c_int64, C.c_int64]; L.primalcr_reference_init.restype = None
+    L.primalcr_write_text_matrix.argtypes = [C.c_char_p, f64p, C.c_int64, C.c_int]
     L.primalcr_predict.argtypes = [f64p, C.c_int64, f64p, C.c_int64, C.c_int, i32p, i32p, C.c_int64, f64p, C.c_int]
     L.primalcr_load_dir.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.primalcr_dataset_info.argtypes = [vp] + [C.POINTER(C.c_int64)] * 4
@@ -151,6 +152,14 @@ def reference_init(n: int, k: int) -> np.ndarray:
     out = np.empty((n, k), np.float64)
     lib().primalcr_reference_init(out.ctypes.data, n, k)
     return out
+
+
+def write_text_matrix(path: str, M: np.ndarray) -> None:
+    """U.txt / V.txt as the reference CLI writes them (pmf-train.cpp:276-295), formatted in parallel on the host."""
+    M = np.ascontiguousarray(M, np.float64)
+    rc = lib().primalcr_write_text_matrix(path.encode(), M.ctypes.data, M.shape[0], M.shape[1])
+    if rc != 0:
+        raise PrimalCRError("primalcr error %d: %s" % (rc, lib().primalcr_last_error().decode()))
 
 
 def load_dir(path: str, threads: int = 0):

@@ -12,6 +12,7 @@
 //     -w model_file : start from the U, V of an existing model file instead of initial()
 #include "../host/driver.hpp"
 #include "../host/loader.hpp"
+#include "../host/textio.hpp"
 
 #include <cstring>
 #include <fstream>
@@ -40,33 +41,7 @@ static void exit_with_help() {
 static double wall() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 static void write_text(const std::string &path, const std::vector<double> &M, long rows, int k) {
-    // pmf-train.cpp:276-295: `myfile << U[i][j]` (6 significant digits), space separated.  The reference streams one number
-    // at a time (minutes for the 3.2 GB of text of the power-law shape); here blocks of rows are formatted
-    // on all host threads and written in order -- byte-identical output (6 s -> well under 1 s for 480,189 x 100).
-    FILE *f = fopen(path.c_str(), "w");
-    if (!f) return;
-    const long block = 4096;
-    const long nblocks = (rows + block - 1) / block;
-    const long wave = 256;                                     // blocks formatted per parallel wave (bounds the memory held)
-    std::vector<std::string> buf((size_t)std::min(wave, std::max(nblocks, 1L)));
-    for (long b0 = 0; b0 < nblocks; b0 += wave) {
-        const long nb = std::min(wave, nblocks - b0);
-#pragma omp parallel for schedule(dynamic, 1)
-        for (long b = 0; b < nb; ++b) {
-            std::string &line = buf[(size_t)b];
-            line.clear();
-            char tmp[64];
-            const long r1 = std::min(rows, (b0 + b + 1) * block);
-            for (long i = (b0 + b) * block; i < r1; ++i)
-                for (int j = 0; j < k; ++j) {
-                    const int n = snprintf(tmp, sizeof(tmp), "%g", M[(size_t)i * k + j]);
-                    line.append(tmp, (size_t)n);
-                    line += (j < k - 1) ? ' ' : '\n';
-                }
-        }
-        for (long b = 0; b < nb; ++b) fwrite(buf[(size_t)b].data(), 1, buf[(size_t)b].size(), f);
-    }
-    fclose(f);
+    pcrhost::write_text_matrix(path.c_str(), M.data(), rows, k);
 }
 
 static void write_matrix(FILE *fp, const std::vector<double> &M, long rows, long k) {   // save_mat_t util.cpp:30-51

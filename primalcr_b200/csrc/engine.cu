@@ -9,6 +9,7 @@
 #include "kernels.h"
 #include "../../include/primalcr.h"
 #include "../host/loader.hpp"
+#include "../host/textio.hpp"
 
 #include <algorithm>
 #include <chrono>
@@ -1438,6 +1439,13 @@ int primalcr_dataset_csr(const primalcr_dataset *ds, int which, const int64_t **
 void primalcr_dataset_free(primalcr_dataset *ds) { delete ds; }
 
 // ---- host utilities -----------------------------------------------------------------------------------
+int primalcr_write_text_matrix(const char *path, const double *M, int64_t rows, int k) {
+    API_BEGIN
+    PCR_REQUIRE(path && (M || rows == 0) && rows >= 0 && k >= 1, "bad argument");
+    if (!pcrhost::write_text_matrix(path, M, (long)rows, k)) throw pcr::Error(PRIMALCR_EARG, std::string("cannot open ") + path);
+    API_END
+}
+
 void primalcr_reference_init(double *out, int64_t n, int64_t k) {
     // initial() util.cpp:80-93: a default-constructed std::default_random_engine per call
     std::default_random_engine generator;

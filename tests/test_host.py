@@ -165,3 +165,25 @@ def test_fast_loader_decimal_parsing_is_correctly_rounded(tmp_path):
     want = np.array([float(t) for t in texts])
     assert a.train.item.tolist() == list(range(len(texts)))
     assert np.array_equal(a.train.rating.view(np.uint64), want.view(np.uint64))
+
+
+def test_text_matrix_writer_is_byte_identical_to_the_reference_stream(tmp_path):
+    """U.txt / V.txt (pmf-train.cpp:276-295): `ofstream << double` at the default precision is printf's %g; the parallel
+    writer must produce the same bytes, row blocks in order, for more rows than one block and awkward values."""
+    rng = np.random.default_rng(5)
+    M = rng.standard_normal((9001, 7)) * 10.0 ** rng.integers(-12, 12, size=(9001, 7))
+    M[0, :] = [0.0, -0.0, 1.0, -1.5, 1e-5, 123456789.0, 0.1]
+    M[1, :3] = [1e300, 5e-324, 999999.5]
+    p = str(tmp_path / "U.txt")
+    api.write_text_matrix(p, M)
+    want = "".join(" ".join("%g" % x for x in row) + "\n" for row in M)
+    assert open(p).read() == want
+    ref = ob.ref_cli("omp-pmf-train")
+    if ref is not None:                      # and the reference CLI itself agrees on the format (tiny run, U.txt side file)
+        ds = dataset("tiny")
+        write_reference_dir(str(tmp_path / "d"), ds)
+        subprocess.run([ref, "-s", "2", "-k", "3", "-t", "0", "-p", "0", "-n", "1", str(tmp_path / "d"), str(tmp_path / "m")],
+                       cwd=tmp_path, check=True, capture_output=True)
+        U, V = load_model(str(tmp_path / "m"))
+        api.write_text_matrix(str(tmp_path / "U_ours.txt"), U)
+        assert open(tmp_path / "U_ours.txt").read() == open(tmp_path / "U.txt").read()

@@ -153,3 +153,65 @@ def test_oracle_vs_live_reference_line_search_branches(stepsize, solver):
     cnt = a["counters"]
     assert all(int(c[1]) > 1 for c in cnt)                                # V line search really took several trials
     assert (int(cnt[0][2]) == 0) == (stepsize > 1e3)                      # ... and was rejected outright with 1e6
+
+
+def test_eval_pair_counts_match_brute_force():
+    """The per-user integer pair-error counts the scale fixtures and the GPU tests rely on (orc_eval's `per_user`), against a
+    literal numpy restatement of util.cpp:467-479 -- including exact score ties, which count as errors."""
+    from tests.util import np_init, to_csr, dataset
+    ds = dataset("tiny")
+    U, V = np_init(ds.d1, ds.d2, 4, seed=1, scale=0.6)
+    V[5] = V[7]; U[3] = 0.0                                  # exact ties
+    out, counts, per_user = ob.oracle().eval(to_csr(ds.train), U, V, 10, want_counts=True)
+    rp = ds.train.row_ptr
+    tot = 0.0; users = 0
+    for u in range(ds.d1):
+        a, b = int(rp[u]), int(rp[u + 1])
+        s = (U[u] * V[ds.train.item[a:b]]).sum(1) if b > a else np.zeros(0)
+        # the oracle accumulates the dot product in the reference's loop order; recompute it the same way for exact ties
+        s = np.array([sum(U[u, t] * V[ds.train.item[e], t] for t in range(U.shape[1])) for e in range(a, b)])
+        v = ds.train.rating[a:b]
+        err = 0
+        for j in range(b - a):
+            for q in range(j + 1, b - a):
+                if (s[j] >= s[q] and v[j] < v[q]) or (s[j] <= s[q] and v[j] > v[q]):
+                    err += 1
+        assert err == per_user[u], u
+        n = b - a
+        if n * (n - 1) // 2 > 0:
+            tot += err / (n * (n - 1) / 2); users += 1
+    assert abs(out[0] - tot / users) < 1e-12
+
+
+@pytest.mark.parametrize("case", ["netflix005", "powerlaw001", "ml1m_pcr"])
+def test_scale_fixtures_are_self_consistent(case):
+    """tests/golden/scale_*.npz (read by the GPU scale tests): the single-threaded restatement and the unmodified reference
+    (race-free objects, all threads) must tell the same story inside the fixture, and the committed generator must still
+    reproduce the data set the fixture was computed on."""
+    import hashlib
+    import os
+    from primalcr_b200.data import synth_dataset
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_%s.npz" % case))
+    iters = int(g["iters"])
+    assert g["obj"].shape == (iters + 1,) and g["counters"].shape == (iters, 8) and g["evals"].shape == (iters + 1, 4)
+    spread = np.abs(g["obj"] - g["ref_obj"]) / np.abs(g["obj"])
+    assert spread[0] < 1e-12 and spread[1] < 1e-10          # iteration 0 / 1: the reference reproduces itself
+    assert spread.max() < (1e-5 if case == "powerlaw001" else 1e-12)
+    assert np.all(np.diff(g["obj"]) < 0)                     # the objective decreases
+    assert np.all(g["counters"][:, 0] <= 10) and np.all(g["counters"][:, 1] <= 20)
+    d1 = int(g["d1"])
+    assert g["err_train"].shape == (iters + 1, d1) and g["collapsed"].shape[0] == iters + 1
+    collapsed = np.unpackbits(g["collapsed"], axis=1)[:, :d1]
+    assert collapsed[0].sum() == 0                           # nobody has collapsed at the N(0,1) init
+    if "ref1_obj" in g:                                       # the unmodified reference on one thread == the restatement, bitwise
+        assert np.array_equal(g["ref1_obj"][1:], g["obj"][1:]) and np.array_equal(g["ref1_evals"], g["evals"])
+    ds = synth_dataset(str(g["shape"]), scale=float(g["scale"]), device="cpu")
+    h = hashlib.sha1()
+    for a in (ds.train.row_ptr, ds.train.item, ds.train.rating, ds.test.row_ptr, ds.test.item, ds.test.rating):
+        h.update(np.ascontiguousarray(a).tobytes())
+    assert h.hexdigest() == str(g["digest"])
+    # the evaluation means stored in the fixture follow from its own per-user integers
+    ln = ds.train.lens().astype(np.float64); pairs = ln * (ln - 1) / 2
+    for i in range(iters + 1):
+        mean = (g["err_train"][i][pairs > 0] / pairs[pairs > 0]).mean()
+        assert abs(mean - g["evals"][i, 0]) < 1e-12
