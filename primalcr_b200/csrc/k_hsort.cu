@@ -10,8 +10,8 @@
 //      tile with coalesced stores.  A user of len ratings needs ceil(log2(ceil(len / 2048))) passes; users that are done
 //      simply have no work in later passes.
 // Order: ascending score, ties (equal as doubles, so -0.0 == +0.0) by original position -- the same total order as the
-// tile kernels and the oracle, hence bit-identical sorted arrays.  The data ping-pongs between the final arrays
-// (SortedMeta::s / pos) and a scratch pair; the starting side is chosen per user so that the last pass lands in the
+// tile kernels (the reference's std::sort is unstable, no output of it depends on the order of ties), hence identical
+// sorted arrays on every path.  The data ping-pongs between the final arrays (SortedMeta::s / pos) and a scratch pair; the starting side is chosen per user so that the last pass lands in the
 // final arrays.  12 bytes per rating and pass; no library call on the path (round 1 used cub::DeviceSegmentedSort here).
 #include "kernels.h"
 #include <math_constants.h>
