@@ -36,9 +36,9 @@ def main():
         out.append("| device time of the SAME iterations 1-25 (`e2e.device_same_window`) -> copies + setup cost %.1f ms per iteration | %.4f s |" % ((e["value"] - e["device_same_window"]) * 1e3, e["device_same_window"]))
         if e.get("shim") and e["shim"].get("value"):
             out.append("| end to end through the real C++ drop-in (`pcrpp(smat_t&, mat_t&, ...)`, reference containers in pageable memory, a fresh process; `e2e.shim`) | %.3f s per iteration (%.2f s for %d iterations) |" % (e["shim"]["value"], e["shim"]["call_seconds"], e["shim"]["iterations"]))
-        if cb:
+        if cb and "value" in cb:
             out.append("| reference CPU (`cpu_baseline`): %s | %.1f s |" % (cb.get("sample", "")[:160], cb["value"]))
-        if par:
+        if par and "obj_rel_err" in par:
             out.append("| in-run parity vs the unmodified reference (%s) | objective %.1e relative, NDCG@10 %.1e, pairwise error %.1e |" % (par.get("sample", "")[:120], par["obj_rel_err"], par["ndcg_abs_err"], par["pairwise_err_abs_err"]))
         out.append("| algorithmic bytes per iteration `B_alg` (SURVEY 8d; %.1f N*k passes, %.1f sort+sweep passes) | %.2f TB |" % (it["counters"]["passes"], it["counters"]["sorts"], it["b_alg_bytes"] / 1e12))
         out.append("| `B_alg / t` vs measured HBM peak %.0f GB/s (`frac_kind: algorithmic_vs_hbm`, not an HBM utilisation) | %.0f GB/s = %.2f x peak |" % (r["peak"], it["achieved"], it["frac"]))
