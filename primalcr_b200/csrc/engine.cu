@@ -1046,7 +1046,7 @@ struct primalcr_engine { Engine *impl; };
 extern "C" {
 
 const char *primalcr_last_error(void) { return pcr::g_last_error.c_str(); }
-const char *primalcr_version(void) { return "primalcr_b200 0.1.0 (sm_100a)"; }
+const char *primalcr_version(void) { return "primalcr_b200 0.2.0 (sm_100a)"; }
 
 void primalcr_default_config(primalcr_config *cfg) {
     if (!cfg) return;
