@@ -26,7 +26,8 @@ def main():
     d = load("r02_bench_netflix_k100_1gpu.json")
     out = ["# profiles/ — round 2 evidence (round-1 files `r01_*` kept for comparison)\n",
            "All numbers: B200 (sm_100a, 148 SMs; SM clocks and throttle reasons sampled during each timed region, `clocks` key), fp64,\n"
-           "Primal-CR++ `-s 2 -l 5000`, reference init, synthetic data of the named shape.  Regenerate: `python tools/make_profiles_readme.py`.\n"]
+           "Primal-CR++ `-s 2 -l 5000`, reference init, synthetic data of the named shape.  Regenerate: `python tools/make_profiles_readme.py`.\n"
+           "What was done about every item of the round-1 review: `r02_verdict_response.md`; measured-and-rejected variants: `experiments/README.md`.\n"]
     if d:
         e = d["e2e"]; r = d["roofline"]; it = r["iteration"]; cb = d.get("cpu_baseline") or {}; par = d.get("parity") or {}
         out.append("## Headline: Netflix-shape (480,189 x 17,770, 100,000,003 ratings), k=100, one B200 — `python bench.py --steps 20 --warmup 5` (the driver's command; `r02_bench_netflix_k100_1gpu.json`)\n")
